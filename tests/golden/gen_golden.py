@@ -1,0 +1,407 @@
+"""Generate tests/golden/golden_v1.npz by EXECUTING THE REFERENCE'S OWN SOURCE.
+
+Run in the build container only (needs /root/reference; never at test time):
+    python tests/golden/gen_golden.py
+
+/root/reference/{renderer,pathtracer}.py and lib/*.py are imported unmodified on top of the
+Taichi stand-in in oracle/ti_shim (Taichi itself is not installable here).  Every value stored
+is the output of a reference @ti.func (file:line in the comments) on seeded inputs; the few
+statements that live in @ti.kernel bodies (struct-for loops cannot be called) are replayed here
+line by line with the kernel line numbers cited.  tests/test_oracle_golden.py then requires
+oracle/de_oracle.c to reproduce every array bit for bit.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = os.environ.get("DE_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(ROOT, "oracle", "ti_shim"))
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(ROOT, "digital-earth_b200"))
+
+import taichi as ti  # noqa: E402  (the shim)
+from taichi.math import vec2, vec3, vec4  # noqa: E402
+import pathtracer as pt  # noqa: E402
+import renderer as rd  # noqa: E402
+import lib.volume_rendering_models as volume  # noqa: E402
+import lib.surface_rendering_models as surface  # noqa: E402
+import lib.colour as colour  # noqa: E402
+import lib.math_utils as mu  # noqa: E402
+import lib.sampling as sampling  # noqa: E402
+import lib.OpenDRT as odrt  # noqa: E402
+import lib.AgX as agx  # noqa: E402
+from lib.parameters import PathParameters, SceneParameters  # noqa: E402
+import synth  # noqa: E402
+
+f32 = np.float32
+TEX_W, TEX_H = 64, 32
+IMG_W, IMG_H = 32, 16
+
+
+# ----------------------------------------------------------------- Philox ---
+def philox4x32_10(ctr, key):
+    c0, c1, c2, c3 = ctr
+    k0, k1 = key
+    for _ in range(10):
+        p0 = 0xD2511F53 * c0
+        p1 = 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c3 ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF
+        k0 = (k0 + 0x9E3779B9) & 0xFFFFFFFF
+        k1 = (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return [c0, c1, c2, c3]
+
+
+class Stream:
+    """key=(seed,pixel) counter=(sample,bounce,draw>>2,0) -- the framework's RNG contract."""
+
+    def __init__(self, seed, pixel, sample):
+        self.key = (seed & 0xFFFFFFFF, pixel & 0xFFFFFFFF)
+        self.sample, self.bounce, self.draw, self.buf = sample, 0, 0, None
+
+    def set_bounce(self, b):
+        self.bounce, self.draw = b, 0
+
+    def __call__(self):
+        if self.draw & 3 == 0:
+            self.buf = philox4x32_10((self.sample, self.bounce, self.draw >> 2, 0), self.key)
+        v = self.buf[self.draw & 3]
+        self.draw += 1
+        return v
+
+
+class ListStream:
+    def __init__(self, vals):
+        self.vals, self.pos = [int(v) for v in vals], 0
+
+    def __call__(self):
+        v = self.vals[self.pos]
+        self.pos += 1
+        return v
+
+
+# ---------------------------------------------------------- scene set-up ---
+def shim_tex(arr_u8, fmt):
+    a = arr_u8 if arr_u8.ndim == 3 else arr_u8[:, :, None]
+    t = ti.Texture(fmt, (a.shape[1], a.shape[0]))
+    t.set_data(a.transpose(1, 0, 2).astype(np.float32) / np.float32(255.0))  # renderer.py:170-210
+    return t
+
+
+def make_renderer(W, H, luts):
+    R = rd.Renderer.__new__(rd.Renderer)  # skip __init__: it reads the NASA PNGs (renderer.py:60-94)
+    R.image_res = (W, H)
+    R.aspect_ratio = W / H
+    R.vignette_strength, R.vignette_radius, R.vignette_center = 0.9, 0.0, [0.5, 0.5]  # renderer.py:20-22
+    for n in ("fov", "aspect_scale", "exposure", "gamma", "sun_angle", "sun_path_rot"):
+        setattr(R, n, ti.field(dtype=ti.f32, shape=()))
+    R.selected_crf = ti.field(dtype=ti.i32, shape=())
+    R.crf_count = ti.field(dtype=ti.i32, shape=())
+    for n in ("camera_pos", "look_at", "up"):
+        setattr(R, n, ti.Vector.field(3, dtype=ti.f32, shape=()))
+    R.land_height_scale = 7800.0  # renderer.py:58
+    R.crf_lut_res = (1024, luts["crf"].shape[0])
+    R.crf_tex = ti.Texture(ti.Format.rgba32f, R.crf_lut_res)
+    R.crf_tex.set_data(luts["crf"].transpose(1, 0, 2))  # (1024, n, 3) as renderer.py:166
+    R.set_crf_count(R.crf_lut_res[1])
+    R.CIE_LUT_tex = ti.Texture(ti.Format.rgba16f, (441, 2))
+    R.CIE_LUT_tex.set_data(luts["cie"].transpose(1, 0, 2))  # renderer.py:101-107 -> [x][y][c]
+    R.srgb_to_spectrum_buff = ti.Vector.field(3, dtype=ti.f16, shape=(300))
+    R.srgb_to_spectrum_buff.from_numpy(luts["srgb2spec"])
+    R.O3_crossec_LUT_buff = ti.field(dtype=ti.f32, shape=(441))
+    R.O3_crossec_LUT_buff.from_numpy(luts["o3"])
+    return R
+
+
+def load_config(path):
+    with open(path) as f:
+        ln = f.read().split("\n")
+    v = [list(map(float, ln[i].split())) for i in range(3)]
+    return dict(cam_pos=v[0], look_at=v[1], up=v[2], fov=float(ln[3]), aspect_scale=float(ln[4]), exposure=float(ln[5]),
+                selected_crf=int(ln[6]), gamma=float(ln[7]), sun_angle=float(ln[8]), sun_path_rot=float(ln[9]))
+
+
+def apply_config(R, cfg):
+    R.set_camera_pos(*cfg["cam_pos"]); R.set_look_at(*cfg["look_at"]); R.set_up(*cfg["up"])
+    R.set_fov(cfg["fov"]); R.set_aspect_scale(cfg["aspect_scale"]); R.set_exposure(cfg["exposure"])
+    R.set_crf(cfg["selected_crf"]); R.set_gamma(cfg["gamma"]); R.set_sun_angle(cfg["sun_angle"]); R.set_sun_path_rot(cfg["sun_path_rot"])
+
+
+def scene_params_of(R):
+    """renderer.py:293-302, statement by statement."""
+    sp = SceneParameters()
+    sp.land_height_scale = R.land_height_scale
+    sun_radius = f32(6.95e8)
+    sun_distance = f32(1.4959e11)
+    sp.sun_angular_radius = sun_radius / sun_distance
+    sp.sun_cos_angle = ti.cos(sp.sun_angular_radius)
+    sun_rot = vec2(-ti.sin(R.sun_path_rot[None]), ti.cos(R.sun_path_rot[None]))
+    sp.light_direction = vec3(-ti.sin(R.sun_angle[None]), ti.cos(R.sun_angle[None]) * sun_rot)
+    return sp
+
+
+def V(a):
+    return vec3(f32(a[0]), f32(a[1]), f32(a[2]))
+
+
+def arr(v):
+    return np.array([float(x) for x in v], dtype=np.float32)
+
+
+def unit(rng, n):
+    d = rng.normal(size=(n, 3))
+    return (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+
+
+def main():
+    t_all = time.time()
+    rng = np.random.default_rng(20261017)
+    G = {}
+    luts = dict(np.load(os.path.join(ROOT, "digital-earth_b200", "assets", "luts.npz")))
+    tex = synth.make_textures(TEX_W, TEX_H, cloud_cover=0.6, seed=7)
+    for k, a in tex.items():
+        G["tex_" + k] = a
+    T = {
+        "albedo": shim_tex(tex["albedo"], ti.Format.rgba8), "topography": shim_tex(tex["topography"], ti.Format.r8),
+        "ocean": shim_tex(tex["ocean"], ti.Format.r8), "clouds": shim_tex(tex["clouds"], ti.Format.r8),
+        "bathymetry": shim_tex(tex["bathymetry"], ti.Format.r8), "emissive": shim_tex(tex["emissive"], ti.Format.r8),
+        "stars": shim_tex(tex["stars"], ti.Format.rgba8),
+    }
+    pt.TOPOGRAPHY_TEX_RES = (TEX_W, TEX_H)  # lib/textures.py constant consumed at pathtracer.py:20
+    R = make_renderer(IMG_W, IMG_H, luts)
+    cfgs = {n: load_config(os.path.join(REF, "config - %s.txt" % n)) for n in ("Apollo 11", "florida", "sunset hurricane")}
+    PR = 6371e3
+
+    # ---- rsi (math_utils.py:17-23)
+    n = 64
+    pos = unit(rng, n) * (PR * (1.0 + rng.random((n, 1)) ** 3 * 8.0)).astype(np.float32)
+    dirs = unit(rng, n)
+    dirs[: n // 2] = (-pos[: n // 2] / np.linalg.norm(pos[: n // 2], axis=1, keepdims=True) + 0.15 * unit(rng, n // 2)).astype(np.float32)
+    dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
+    rr = rng.choice(np.array([6371e3, 6481e3, 6375e3, 6381e3], np.float32), n)
+    G["rsi_pos"], G["rsi_dir"], G["rsi_r"] = pos, dirs, rr
+    G["rsi_out"] = np.stack([arr(mu.rsi(V(pos[i]), V(dirs[i]), f32(rr[i]))) for i in range(n)])
+
+    # ---- densities (volume_rendering_models.py:229-277)
+    h = np.concatenate([[-50.0, 0.0, 1300.0, 1300.5, 2400.0, 2400.5, 11500.0, 11501.0, 25000.0], rng.random(55) ** 2 * 120000.0]).astype(np.float32)
+    G["density_h"] = h
+    G["density_out"] = np.stack([arr(volume.get_density(f32(x))) for x in h])
+
+    # ---- spectra on the 256 wavelength bins (volume_rendering_models.py:194-224, colour.py:51-60)
+    wl = np.array([f32(390.0) + f32(441.0) * f32((2 * k + 1) / 512.0) for k in range(256)], dtype=np.float32)
+    G["spectra_wl"] = wl
+    G["spectra_out"] = np.array([[volume.spectra_extinction_rayleigh(f32(w)), volume.spectra_extinction_mie(f32(w)),
+                                  volume.spectra_extinction_ozone(f32(w), R.O3_crossec_LUT_buff),
+                                  colour.plancks(5778.0, f32(w)), colour.plancks(2700.0, f32(w))] for w in wl], dtype=np.float32)
+
+    # ---- phase evaluation (pathtracer.py:235-247)
+    n = 96
+    a, b = unit(rng, n), unit(rng, n)
+    b[:24] = (a[:24] + 0.02 * unit(rng, 24)); b = (b / np.linalg.norm(b, axis=1, keepdims=True)).astype(np.float32)
+    ids = rng.choice(np.array([0, 1, 3, 4], np.int32), n)
+    red = rng.integers(0, 2, n).astype(np.int32)
+    G["phase_a"], G["phase_b"], G["phase_id"], G["phase_reduce"] = a, b, ids, red
+    G["phase_eval_out"] = np.array([pt.evaluate_phase(V(a[i]), V(b[i]), int(ids[i]), bool(red[i])) for i in range(n)], dtype=np.float32)
+
+    # ---- phase sampling with explicit draws (pathtracer.py:249-261)
+    rnd = rng.integers(0, 2 ** 32, (n, 4), dtype=np.uint64).astype(np.uint32)
+    G["phase_rand"] = rnd
+    od, ow = [], []
+    for i in range(n):
+        ti._set_random_source(ListStream(rnd[i]))
+        d, w = pt.sample_phase(V(a[i]), int(ids[i]), bool(red[i]))
+        od.append(arr(d)); ow.append(f32(w))
+    G["phase_sample_dir"], G["phase_sample_w"] = np.stack(od), np.array(ow, np.float32)
+
+    # ---- direction samplers (sampling.py:25-39)
+    nn = unit(rng, 48); nn[0] = (0, 1, 0); nn[1] = (0.2, 0.95, 0.1); nn[1] /= np.linalg.norm(nn[1])
+    r2 = rng.integers(0, 2 ** 32, (48, 2), dtype=np.uint64).astype(np.uint32)
+    G["dirs_n"], G["dirs_rand"] = nn, r2
+    cmax = ti.cos(f32(6.95e8) / f32(1.4959e11))
+    G["dirs_cmax"] = np.float32(cmax)
+    o0, o1 = [], []
+    for i in range(48):
+        ti._set_random_source(ListStream(r2[i])); o0.append(arr(sampling.sample_cone_oriented(cmax, V(nn[i]))))
+        ti._set_random_source(ListStream(r2[i])); o1.append(arr(sampling.sample_hemisphere_cosine_weighted(V(nn[i]))))
+    G["dirs_cone_out"], G["dirs_hemi_out"] = np.stack(o0), np.stack(o1)
+
+    # ---- earth_brdf (surface_rendering_models.py:9-37)
+    n = 64
+    nr = unit(rng, n)
+    vv = unit(rng, n); vv = np.where(((vv * nr).sum(1) < 0)[:, None], -vv, vv)
+    ll = unit(rng, n); ll[: n - 8] = np.where(((ll[: n - 8] * nr[: n - 8]).sum(1) < 0)[:, None], -ll[: n - 8], ll[: n - 8])
+    alb, oc, ba = rng.random(n).astype(np.float32), rng.random(n).astype(np.float32), rng.random(n).astype(np.float32)
+    oc[:8] = 1.0; oc[8:16] = 0.0
+    G["brdf_albedo"], G["brdf_ocean"], G["brdf_bathy"], G["brdf_v"], G["brdf_n"], G["brdf_l"] = alb, oc, ba, vv, nr, ll
+    G["brdf_out"] = np.array([[float(x) for x in surface.earth_brdf(f32(alb[i]), f32(oc[i]), f32(ba[i]), V(vv[i]), V(nr[i]), V(ll[i]))] for i in range(n)], np.float32)
+
+    # ---- srgb_to_spectrum (colour.py:62-71)
+    n = 64
+    rgb = rng.random((n, 3)).astype(np.float32)
+    w2 = np.concatenate([wl[rng.integers(0, 256, n - 6)], np.array([399.5, 400.2, 401.0, 698.9, 699.4, 700.1], np.float32)])
+    G["s2s_rgb"], G["s2s_wl"] = rgb, w2
+    G["s2s_out"] = np.array([colour.srgb_to_spectrum(R.srgb_to_spectrum_buff, V(rgb[i]), f32(w2[i])) for i in range(n)], np.float32)
+
+    # ---- spectrum_sample (colour.py:12-48)
+    n = 96
+    r1 = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32); r1[0] = 0; r1[1] = 0xFFFFFFFF
+    G["specsample_rand"] = r1
+    out = []
+    for i in range(n):
+        ti._set_random_source(ListStream([r1[i]]))
+        w_, resp, rcp = colour.spectrum_sample(R.CIE_LUT_tex, 441)
+        out.append([w_, resp.x, resp.y, resp.z, rcp])
+    G["specsample_out"] = np.array(out, np.float32)
+
+    # ---- sample_sphere_texture (math_utils.py:38-44)
+    n = 64
+    p = unit(rng, n) * f32(6.4e6); p[0] = (0, 6.4e6, 0); p[1] = (-6.4e6, 0, 1e-3); p[2] = (-6.4e6, 0, -1e-3)
+    G["texfetch_pos"] = p
+    G["texfetch_r8_out"] = np.stack([arr(mu.sample_sphere_texture(T["clouds"], V(p[i]))) for i in range(n)])
+    G["texfetch_rgb8_out"] = np.stack([arr(mu.sample_sphere_texture(T["albedo"], V(p[i]))) for i in range(n)])
+
+    # ---- get_cast_dir (renderer.py:269-279), three shipped configs
+    for cname, cfg in cfgs.items():
+        apply_config(R, cfg)
+        key = cname.split()[0].lower()
+        us = rng.integers(0, IMG_W, 16); vs = rng.integers(0, IMG_H, 16)
+        rr2 = rng.integers(0, 2 ** 32, (16, 2), dtype=np.uint64).astype(np.uint32)
+        o = []
+        for i in range(16):
+            ti._set_random_source(ListStream(rr2[i]))
+            o.append(arr(R.get_cast_dir(ti.I32(int(us[i])), ti.I32(int(vs[i])))))
+        G["cast_%s_u" % key], G["cast_%s_v" % key], G["cast_%s_rand" % key], G["cast_%s_out" % key] = us.astype(np.float32), vs.astype(np.float32), rr2, np.stack(o)
+
+    # ---- tonemap chain (OpenDRT.py:221-484, AgX.py:131-160, renderer.py:333-365, colour.py:74-79)
+    n = 96
+    c = (rng.random((n, 3)) ** 3 * np.array([4.0, 3.0, 5.0])).astype(np.float32)
+    c[0] = (0.18, 0.18, 0.18); c[1] = (64, 64, 64); c[2] = (0, 0, 0); c[3] = (1e-5, 2e-5, 0.5); c[4] = (-0.01, 0.2, 0.1); c[5] = (100.0, 0.1, 0.1)
+    G["tm_rgb"] = c
+    G["opendrt_out"] = np.stack([arr(odrt.openDR_transform(f32(x[0]), f32(x[1]), f32(x[2]))) for x in c])
+    G["agx_out"] = np.stack([arr(agx.display_transform(V(x))) for x in c])
+    t01 = rng.random((n, 3)).astype(np.float32); t01[0] = (0, 0.5, 1); t01[1] = (-0.5, 1.5, 0.999999)
+    G["crf_rgb"] = t01
+    for sel in (0, 5, 12):
+        R.set_crf(sel)
+        G["crf_out_%d" % sel] = np.stack([arr(R.camera_response(R.crf_tex, V(x))) for x in t01])
+    lin = np.concatenate([[0.0, 0.0031308, 0.0031309, 1.0, -0.1], rng.random(59)]).astype(np.float32)
+    G["oetf_in"] = lin
+    G["oetf_out"] = np.array([colour.srgb_transfer(vec3(f32(x), f32(x), f32(x))).x for x in lin], np.float32)
+    # _render_to_image replayed (renderer.py:348-365)
+    apply_config(R, cfgs["Apollo 11"])
+    acc = (rng.random((IMG_H, IMG_W, 3)) ** 2 * 40.0).astype(np.float32)
+    samples = ti.I32(13)
+    res = np.zeros_like(acc)
+    for j in range(IMG_H):
+        for i in range(IMG_W):
+            u = f32(1.0) * f32(i) / f32(R.image_res[0])  # i32 loop index promoted to f32 (renderer.py:349-350)
+            v = f32(1.0) * f32(j) / f32(R.image_res[1])
+            du_, dv_ = u - R.vignette_center[0], v - R.vignette_center[1]  # `**2` is an integer power: Taichi demotes it to x*x
+            darken = 1.0 - R.vignette_strength * ti.max((ti.sqrt(du_ * du_ + dv_ * dv_) - R.vignette_radius), 0)
+            linear = V(acc[j, i]) / samples * darken * ti.pow(2.0, R.exposure[None])
+            tonemapped = odrt.openDR_transform(linear.r, linear.g, linear.b)
+            camera = R.camera_response(R.crf_tex, tonemapped)
+            gamma = ti.pow(camera, R.gamma[None])
+            res[j, i] = arr(colour.srgb_transfer(gamma))
+    G["resolve_accum"], G["resolve_samples"], G["resolve_out"] = acc, np.int32(13), res
+
+    # ---- geometry (pathtracer.py:11-71, 145-169)
+    hs = f32(7800.0)
+    n = 48
+    cam = np.array(cfgs["florida"]["cam_pos"], np.float32)
+    gp = np.tile(cam, (n, 1)); gd = (-gp / np.linalg.norm(gp, axis=1, keepdims=True) + 0.45 * unit(rng, n)).astype(np.float32)
+    gd = (gd / np.linalg.norm(gd, axis=1, keepdims=True)).astype(np.float32)
+    gp[24:] = unit(rng, 24) * f32(6371e3 + 9000.0); gd[24:] = unit(rng, 24)
+    G["geo_pos"], G["geo_dir"] = gp, gd
+    il = np.array([pt.intersect_land(T["topography"], V(gp[i]), V(gd[i]), hs) for i in range(n)], np.float32)
+    G["intersect_land_out"] = il
+    sp_ = unit(rng, 32) * (f32(6371e3) + (rng.random((32, 1)) * 9000.0).astype(np.float32))
+    G["surf_pos"] = sp_.astype(np.float32)
+    G["land_normal_out"] = np.stack([arr(pt.land_normal(T["topography"], V(x), hs)) for x in G["surf_pos"]])
+    G["land_material_out"] = np.array([[*arr(m[0]), m[1], m[2], m[3]] for m in
+                                       (pt.get_land_material(T["albedo"], T["ocean"], T["bathymetry"], T["emissive"], V(x)) for x in G["surf_pos"])], np.float32)
+    cp = unit(rng, 64) * (f32(6371e3) + (rng.random((64, 1)) * 14000.0).astype(np.float32)); cp = cp.astype(np.float32)
+    cp[:8] = np.tile(cam, (8, 1))
+    cd = unit(rng, 64); cd[:8] = gd[:8]
+    cl = np.where(rng.random(64) < 0.5, -1.0, rng.random(64) * 1e5).astype(np.float32)
+    G["cloud_pos"], G["cloud_dir"], G["cloud_land"] = cp, cd, cl
+    G["cloud_limits_out"] = np.array([[float(x) for x in pt.intersect_cloud_limits(V(cp[i]), V(cd[i]), f32(cl[i]))] for i in range(64)], np.float32)
+    G["clouds_density_out"] = np.array([pt.get_clouds_density(T["clouds"], V(cp[i])) for i in range(64)], np.float32)
+
+    # ---- fixed-ray optical depth (pathtracer.py:471-500)
+    n = 48
+    rp = unit(rng, n) * (f32(6371e3) + (rng.random((n, 1)) * 60000.0 + 10.0).astype(np.float32)); rp = rp.astype(np.float32)
+    rdir = unit(rng, n)
+    ex = np.stack([G["spectra_out"][rng.integers(0, 256), :3] for _ in range(n)]).astype(np.float32)
+    G["rm_pos"], G["rm_dir"], G["rm_ext"] = rp, rdir, ex
+    G["rm_out"] = np.array([pt.ray_march_transmittance(V(rp[i]), V(rdir[i]), V(ex[i])) for i in range(n)], np.float32)
+
+    # ---- stochastic sub-paths on the Philox stream (pathtracer.py:172-232)
+    n = 40
+    tp = np.concatenate([gp[:20], cp[8:28]]).astype(np.float32)
+    td = np.concatenate([gd[:20], cd[8:28]]).astype(np.float32)
+    tl = np.concatenate([il[:20], np.full(20, -1.0, np.float32)]).astype(np.float32)
+    tw = wl[rng.integers(0, 256, n)]
+    G["trk_pos"], G["trk_dir"], G["trk_land"], G["trk_wl"], G["trk_seed"] = tp, td, tl, tw, np.uint32(99)
+    d0 = volume.get_density(f32(0.0)); o3m = volume.get_ozone_density(f32(25000.0))
+    si, st = [], []
+    for i in range(n):
+        ext = vec4(volume.spectra_extinction_rayleigh(f32(tw[i])), volume.spectra_extinction_mie(f32(tw[i])),
+                   volume.spectra_extinction_ozone(f32(tw[i]), R.O3_crossec_LUT_buff), f32(volume.clouds_extinct))
+        mr = (ext.xyz * vec3(d0.x, d0.y, o3m)).sum(); mc = ext.w * f32(volume.clouds_density)  # pathtracer.py:355-356
+        s_ = Stream(99, i, 0); s_.set_bounce(1); ti._set_random_source(s_)
+        ev, t_, id_ = pt.sample_interaction(V(tp[i]), V(td[i]), f32(tl[i]), ext, mr, mc, T["clouds"])
+        si.append([float(ev), float(t_), float(id_)])
+        s_ = Stream(99, i, 0); s_.set_bounce(1); ti._set_random_source(s_)
+        st.append([float(pt.sample_transmittance(V(tp[i]), V(td[i]), f32(tl[i]), ext, mr, mc, T["clouds"])), 0.0, 0.0])
+    G["trk_interaction_out"], G["trk_transmittance_out"] = np.array(si, np.float32), np.array(st, np.float32)
+
+    # ---- full path samples: Renderer.render body (renderer.py:305-330) on the three configs
+    orig_si = pt.sample_interaction
+    cur = {}
+
+    def hooked(*a, **k):  # one call per path segment (pathtracer.py:362) -> advance the bounce key
+        cur["s"].set_bounce(cur["s"].bounce + 1)
+        return orig_si(*a, **k)
+    pt.sample_interaction = hooked
+    n_per = int(os.environ.get("DE_GOLDEN_PATHS", "40"))
+    for cname, cfg in cfgs.items():
+        key = cname.split()[0].lower()
+        apply_config(R, cfg)
+        sp = scene_params_of(R)
+        px = rng.integers(0, IMG_W, n_per); py = rng.integers(0, IMG_H, n_per); sm = rng.integers(0, 4, n_per)
+        outs = []
+        t0 = time.time()
+        for i in range(n_per):
+            s_ = Stream(5, int(py[i]) * IMG_W + int(px[i]), int(sm[i])); cur["s"] = s_; ti._set_random_source(s_)
+            wavelength, response, rcp = colour.spectrum_sample(R.CIE_LUT_tex, 441)  # renderer.py:310
+            pp = PathParameters()
+            pp.wavelength = wavelength
+            pp.ray_dir = R.get_cast_dir(ti.I32(int(px[i])), ti.I32(int(py[i])))  # :313
+            pp.ray_pos = R.camera_pos[None]  # :314
+            L = pt.path_tracer(pp, sp, T["albedo"], T["topography"], T["ocean"], T["clouds"], T["bathymetry"], T["emissive"], T["stars"],
+                               R.srgb_to_spectrum_buff, R.O3_crossec_LUT_buff)  # :317
+            xyz = L * response * rcp  # :329
+            rgbc = colour.xyzToRGBMatrix_D65 @ xyz  # :330
+            outs.append([*arr(rgbc), wavelength, L])
+        print("paths %-8s %d in %.1fs" % (key, n_per, time.time() - t0), flush=True)
+        G["path_%s_px" % key], G["path_%s_py" % key], G["path_%s_sample" % key] = px.astype(np.int32), py.astype(np.int32), sm.astype(np.uint32)
+        G["path_%s_out" % key] = np.array(outs, np.float32)
+        for k2 in ("cam_pos", "look_at", "up"):
+            G["cfg_%s_%s" % (key, k2)] = np.array(cfg[k2], np.float64)
+        G["cfg_%s_scalars" % key] = np.array([cfg[k2] for k2 in ("fov", "aspect_scale", "exposure", "selected_crf", "gamma", "sun_angle", "sun_path_rot")], np.float64)
+    pt.sample_interaction = orig_si
+    G["path_seed"] = np.uint32(5)
+    G["img_res"] = np.array([IMG_W, IMG_H], np.int32)
+    # Random123 known-answer vectors for Philox4x32-10
+    G["philox_kat"] = np.array([philox4x32_10((0, 0, 0, 0), (0, 0)), philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2),
+                                philox4x32_10((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0))], np.uint32)
+    outp = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
+    np.savez_compressed(outp, **G)
+    print("wrote %s (%d arrays, %.1f kB) in %.1fs" % (outp, len(G), os.path.getsize(outp) / 1e3, time.time() - t_all))
+
+
+if __name__ == "__main__":
+    main()
