@@ -1,0 +1,339 @@
+// de_api.cu -- the C-ABI of libde.so (include/de_api.h): context, uploads, dispatch.
+// Host code only; every piece of arithmetic on the render path runs in the device TUs.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/de_api.h"
+#include "de_launch.h"
+#include "de_wavefront.h"
+
+struct de_ctx {
+    int device = 0, W = 0, H = 0, mode = DE_MODE_WAVEFRONT;
+    cudaStream_t stream = nullptr;
+    bool have_params = false, have_luts = false, counting = false, derived_dirty = true;
+    bool have_tex[DE_TEX_COUNT] = {};
+    DeParams params{};
+    DevScene scene{};
+    uint8_t *d_tex[DE_TEX_COUNT] = {};
+    cudaArray_t arr[DE_TEX_COUNT] = {};
+    float *d_cie = nullptr, *d_s2s = nullptr, *d_o3 = nullptr, *d_crf = nullptr, *d_cdf = nullptr;
+    LambdaRow *d_lam = nullptr;
+    DevDerived *d_derived = nullptr;
+    float *d_accum = nullptr, *d_image = nullptr;
+    unsigned long long *d_counters = nullptr;
+    DeWavefrontState *wf = nullptr;
+    std::string err;
+};
+
+namespace {
+int fail(de_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    return code;
+}
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) return fail(ctx, DE_ERR_CUDA, std::string(#call ": ") + cudaGetErrorString(e_)); \
+    } while (0)
+#define NEED(cond, msg) do { if (!(cond)) return fail(ctx, DE_ERR_INVALID, msg); } while (0)
+#define ENTER()                                                  \
+    if (!ctx) return DE_ERR_INVALID;                             \
+    CU(cudaSetDevice(ctx->device))
+
+int check_launch(de_ctx *ctx, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DE_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return DE_OK;
+}
+
+// keep the by-value kernel argument in sync with params + uploads
+int refresh_scene(de_ctx *ctx) {
+    DevScene &s = ctx->scene;
+    const DeParams &p = ctx->params;
+    s.cam_pos = make_float3(p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]);
+    s.look_at = make_float3(p.look_at[0], p.look_at[1], p.look_at[2]);
+    s.up = make_float3(p.up[0], p.up[1], p.up[2]);
+    s.fov = p.fov; s.aspect_scale = p.aspect_scale; s.sun_angle = p.sun_angle; s.sun_path_rot = p.sun_path_rot;
+    s.aspect_ratio = (float)((double)ctx->W / (double)ctx->H);  // renderer.py:19 (Python float -> f32 at use)
+    s.land_height_scale = p.land_height_scale; s.exposure = p.exposure; s.gamma = p.gamma;
+    s.selected_crf = p.selected_crf; s.crf_count = p.crf_count > 0 ? p.crf_count : s.n_crf;
+    s.vig_strength = p.vignette_strength; s.vig_radius = p.vignette_radius; s.vig_cx = p.vignette_center[0]; s.vig_cy = p.vignette_center[1];
+    s.tonemapper = p.tonemapper;
+    s.topo_tex_w = p.topo_tex_w > 0 ? p.topo_tex_w : s.tex[DE_TEX_TOPOGRAPHY].w;
+    s.W = ctx->W; s.H = ctx->H;
+    s.derived = ctx->d_derived; s.lam = ctx->d_lam; s.cdf = ctx->d_cdf;
+    s.cie = ctx->d_cie; s.s2s = ctx->d_s2s; s.o3 = ctx->d_o3; s.crf = ctx->d_crf;
+    s.counters = ctx->counting ? ctx->d_counters : nullptr;
+    if (ctx->derived_dirty && ctx->have_params && s.topo_tex_w > 0) {
+        de_exact::launch_prepare(s, ctx->d_derived, ctx->stream);
+        int rc = check_launch(ctx, "prepare");
+        if (rc) return rc;
+        ctx->derived_dirty = false;
+    }
+    return DE_OK;
+}
+int ready_to_render(de_ctx *ctx) {
+    if (!ctx->have_params) return fail(ctx, DE_ERR_STATE, "de_set_params has not been called");
+    if (!ctx->have_luts) return fail(ctx, DE_ERR_STATE, "de_upload_luts has not been called");
+    for (int i = 0; i < DE_TEX_COUNT; ++i)
+        if (!ctx->have_tex[i]) return fail(ctx, DE_ERR_STATE, "texture slot " + std::to_string(i) + " has not been uploaded");
+    return refresh_scene(ctx);
+}
+}  // namespace
+
+extern "C" {
+
+int de_abi_version(void) { return DE_ABI_VERSION; }
+
+int de_create(de_ctx **out, int device, int width, int height) {
+    if (!out) return DE_ERR_INVALID;
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || width % 16 != 0 || height % 8 != 0) return DE_ERR_INVALID;  // renderer.py:46
+    de_ctx *ctx = new (std::nothrow) de_ctx();
+    if (!ctx) return DE_ERR_NOMEM;
+    ctx->device = device; ctx->W = width; ctx->H = height;
+    auto bail = [&](cudaError_t e) { (void)e; de_destroy(ctx); return DE_ERR_CUDA; };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e);
+    size_t npx = (size_t)width * height;
+    if ((e = cudaMalloc(&ctx->d_accum, npx * 3 * sizeof(float))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->d_image, npx * 3 * sizeof(float))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->d_derived, sizeof(DevDerived))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->d_lam, sizeof(LambdaRow) * 512)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->d_cdf, sizeof(float) * 512)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->d_counters, sizeof(DeCounters))) != cudaSuccess) return bail(e);
+    if ((e = cudaMemset(ctx->d_accum, 0, npx * 3 * sizeof(float))) != cudaSuccess) return bail(e);
+    if ((e = cudaMemset(ctx->d_counters, 0, sizeof(DeCounters))) != cudaSuccess) return bail(e);
+    *out = ctx;
+    return DE_OK;
+}
+
+void de_destroy(de_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < DE_TEX_COUNT; ++i) {
+        if (ctx->scene.tex[i].obj) cudaDestroyTextureObject(ctx->scene.tex[i].obj);
+        if (ctx->arr[i]) cudaFreeArray(ctx->arr[i]);
+        cudaFree(ctx->d_tex[i]);
+    }
+    de_wavefront_free(ctx->wf);
+    cudaFree(ctx->d_cie); cudaFree(ctx->d_s2s); cudaFree(ctx->d_o3); cudaFree(ctx->d_crf); cudaFree(ctx->d_cdf);
+    cudaFree(ctx->d_lam); cudaFree(ctx->d_derived); cudaFree(ctx->d_accum); cudaFree(ctx->d_image); cudaFree(ctx->d_counters);
+    delete ctx;
+}
+
+const char *de_last_error(de_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int de_set_stream(de_ctx *ctx, void *cuda_stream) {
+    ENTER();
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return DE_OK;
+}
+int de_set_mode(de_ctx *ctx, int mode) {
+    ENTER();
+    NEED(mode >= DE_MODE_WAVEFRONT && mode <= DE_MODE_PARITY, "unknown mode");
+    ctx->mode = mode;
+    return DE_OK;
+}
+int de_set_counting(de_ctx *ctx, int enabled) {
+    ENTER();
+    ctx->counting = enabled != 0;
+    return DE_OK;
+}
+
+int de_set_params(de_ctx *ctx, const DeParams *p) {
+    ENTER();
+    NEED(p, "params is NULL");
+    NEED(p->selected_crf >= 0, "selected_crf < 0");
+    ctx->params = *p;
+    ctx->have_params = true;
+    ctx->derived_dirty = true;
+    return DE_OK;
+}
+
+int de_upload_texture(de_ctx *ctx, int slot, const uint8_t *host, int w, int h, int channels) {
+    ENTER();
+    NEED(slot >= 0 && slot < DE_TEX_COUNT, "bad texture slot");
+    NEED(host && w > 0 && h > 0, "bad texture");
+    bool rgb = slot == DE_TEX_ALBEDO || slot == DE_TEX_STARS;
+    NEED(channels == (rgb ? 3 : 1), "albedo/stars take 3 channels, the other maps 1");
+    size_t bytes = (size_t)w * h * channels;
+    DevTex &t = ctx->scene.tex[slot];
+    if (t.obj) { cudaDestroyTextureObject(t.obj); t.obj = 0; }
+    if (ctx->arr[slot]) { cudaFreeArray(ctx->arr[slot]); ctx->arr[slot] = nullptr; }
+    cudaFree(ctx->d_tex[slot]); ctx->d_tex[slot] = nullptr;
+    CU(cudaMalloc(&ctx->d_tex[slot], bytes));
+    CU(cudaMemcpyAsync(ctx->d_tex[slot], host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // block-linear copy behind a point-sampled, clamped, unnormalised-coordinate texture object:
+    // the TEX path of the wavefront integrator gathers the 2x2 footprint with one instruction.
+    cudaChannelFormatDesc fd = rgb ? cudaCreateChannelDesc<uchar4>() : cudaCreateChannelDesc<unsigned char>();
+    CU(cudaMallocArray(&ctx->arr[slot], &fd, (size_t)w, (size_t)h, cudaArrayTextureGather));
+    if (rgb) {
+        std::vector<uint8_t> rgba((size_t)w * h * 4);
+        for (size_t i = 0; i < (size_t)w * h; ++i) { rgba[4 * i] = host[3 * i]; rgba[4 * i + 1] = host[3 * i + 1]; rgba[4 * i + 2] = host[3 * i + 2]; rgba[4 * i + 3] = 0; }
+        CU(cudaMemcpy2DToArray(ctx->arr[slot], 0, 0, rgba.data(), (size_t)w * 4, (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice));
+    } else {
+        CU(cudaMemcpy2DToArray(ctx->arr[slot], 0, 0, host, (size_t)w, (size_t)w, (size_t)h, cudaMemcpyHostToDevice));
+    }
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = ctx->arr[slot];
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    CU(cudaCreateTextureObject(&t.obj, &rd, &td, nullptr));
+    t.data = ctx->d_tex[slot]; t.w = w; t.h = h; t.c = channels;
+    ctx->have_tex[slot] = true;
+    if (slot == DE_TEX_TOPOGRAPHY) ctx->derived_dirty = true;
+    CU(cudaStreamSynchronize(ctx->stream));  // host buffer may be released by the caller
+    return DE_OK;
+}
+
+int de_upload_luts(de_ctx *ctx, const float *cie, const uint16_t *s2s, const float *o3, const float *crf, int n_crf) {
+    ENTER();
+    NEED(cie && s2s && o3 && crf && n_crf > 0, "bad LUT arguments");
+    // rgba16f CIE texture (renderer.py:97,212-216): quantise to fp16 once, keep as f32
+    std::vector<float> cie_q(2 * 441 * 3), s2s_f(300 * 3);
+    for (size_t i = 0; i < cie_q.size(); ++i) cie_q[i] = __half2float(__float2half_rn(cie[i]));
+    for (size_t i = 0; i < s2s_f.size(); ++i) { __half_raw r; r.x = s2s[i]; s2s_f[i] = __half2float(__half(r)); }
+    cudaFree(ctx->d_cie); cudaFree(ctx->d_s2s); cudaFree(ctx->d_o3); cudaFree(ctx->d_crf);
+    ctx->d_cie = ctx->d_s2s = ctx->d_o3 = ctx->d_crf = nullptr;
+    CU(cudaMalloc(&ctx->d_cie, cie_q.size() * 4)); CU(cudaMalloc(&ctx->d_s2s, s2s_f.size() * 4));
+    CU(cudaMalloc(&ctx->d_o3, 441 * 4)); CU(cudaMalloc(&ctx->d_crf, (size_t)n_crf * 1024 * 3 * 4));
+    CU(cudaMemcpy(ctx->d_cie, cie_q.data(), cie_q.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_s2s, s2s_f.data(), s2s_f.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_o3, o3, 441 * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_crf, crf, (size_t)n_crf * 1024 * 3 * 4, cudaMemcpyHostToDevice));
+    ctx->scene.n_crf = n_crf;
+    ctx->scene.cie = ctx->d_cie; ctx->scene.s2s = ctx->d_s2s; ctx->scene.o3 = ctx->d_o3; ctx->scene.crf = ctx->d_crf;
+    de_exact::launch_build_lambda(ctx->scene, ctx->d_lam, ctx->d_cdf, ctx->stream);
+    int rc = check_launch(ctx, "build_lambda");
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_luts = true;
+    return DE_OK;
+}
+
+int de_reset(de_ctx *ctx) {
+    ENTER();
+    CU(cudaMemsetAsync(ctx->d_accum, 0, (size_t)ctx->W * ctx->H * 3 * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeCounters), ctx->stream));
+    return DE_OK;
+}
+
+int de_accumulate(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h) {
+    ENTER();
+    NEED(n_spp > 0, "n_spp <= 0");
+    NEED(x0 >= 0 && y0 >= 0 && w > 0 && h > 0 && x0 + w <= ctx->W && y0 + h <= ctx->H, "window outside the frame");
+    int rc = ready_to_render(ctx);
+    if (rc) return rc;
+    if (ctx->mode == DE_MODE_PARITY) de_exact::launch_render_mega(ctx->scene, ctx->d_accum, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
+    else if (ctx->mode == DE_MODE_MEGAKERNEL) de_fast::launch_render_mega(ctx->scene, ctx->d_accum, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
+    else {
+        if (!ctx->wf) {
+            ctx->wf = de_wavefront_alloc(ctx->device);
+            if (!ctx->wf) return fail(ctx, DE_ERR_NOMEM, "wavefront state allocation failed");
+        }
+        de_wavefront_render(ctx->wf, ctx->scene, ctx->d_accum, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
+    }
+    return check_launch(ctx, "render");
+}
+
+int de_get_accum(de_ctx *ctx, float **dev_ptr) {
+    ENTER();
+    NEED(dev_ptr, "dev_ptr is NULL");
+    *dev_ptr = ctx->d_accum;
+    return DE_OK;
+}
+
+int de_resolve(de_ctx *ctx, const float *accum_override, float *dev_out, int spp_total) {
+    ENTER();
+    NEED(dev_out, "dev_out is NULL");
+    NEED(spp_total > 0, "spp_total <= 0");
+    if (!ctx->have_params || !ctx->have_luts) return fail(ctx, DE_ERR_STATE, "params / LUTs missing");
+    int rc = refresh_scene(ctx);
+    if (rc) return rc;
+    const float *src = accum_override ? accum_override : ctx->d_accum;
+    if (ctx->mode == DE_MODE_PARITY) de_exact::launch_resolve(ctx->scene, src, dev_out, spp_total, ctx->stream);
+    else de_fast::launch_resolve(ctx->scene, src, dev_out, spp_total, ctx->stream);
+    return check_launch(ctx, "resolve");
+}
+
+int de_fetch_image_host(de_ctx *ctx, float *host_out, int spp_total) {
+    ENTER();
+    NEED(host_out, "host_out is NULL");
+    int rc = de_resolve(ctx, nullptr, ctx->d_image, spp_total);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(host_out, ctx->d_image, (size_t)ctx->W * ctx->H * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
+int de_sync(de_ctx *ctx) {
+    ENTER();
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
+int de_get_counters(de_ctx *ctx, DeCounters *out) {
+    ENTER();
+    NEED(out, "out is NULL");
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(out, ctx->d_counters, sizeof(DeCounters), cudaMemcpyDeviceToHost));
+    return DE_OK;
+}
+
+// ---------------------------------------------------------------- test hooks
+#define HOOK_PRE(needs_scene)                                                    \
+    ENTER();                                                                     \
+    NEED(n >= 0, "n < 0");                                                       \
+    if (n == 0) return DE_OK;                                                    \
+    if (needs_scene) { int rc_ = refresh_scene(ctx); if (rc_) return rc_; }
+#define HOOK_POST(name) return check_launch(ctx, name)
+
+int de_test_philox(de_ctx *ctx, const uint32_t *in6, uint32_t *out4, int n) { HOOK_PRE(false); de_exact::t_philox(in6, out4, n, ctx->stream); HOOK_POST("philox"); }
+int de_test_rsi(de_ctx *ctx, const float *pos, const float *dir, const float *r, float *out, int n) { HOOK_PRE(false); de_exact::t_rsi(pos, dir, r, out, n, ctx->stream); HOOK_POST("rsi"); }
+int de_test_density(de_ctx *ctx, const float *h, float *out, int n) { HOOK_PRE(false); de_exact::t_density(h, out, n, ctx->stream); HOOK_POST("density"); }
+int de_test_spectra(de_ctx *ctx, const float *wl, float *out, int n) { HOOK_PRE(true); de_exact::t_spectra(ctx->scene, wl, out, n, ctx->stream); HOOK_POST("spectra"); }
+int de_test_phase_eval(de_ctx *ctx, const float *a, const float *b, const int32_t *id, const int32_t *red, float *out, int n) { HOOK_PRE(false); de_exact::t_phase_eval(a, b, id, red, out, n, ctx->stream); HOOK_POST("phase_eval"); }
+int de_test_phase_sample(de_ctx *ctx, const float *a, const int32_t *id, const int32_t *red, const uint32_t *rand, float *od, float *ow, int n) { HOOK_PRE(false); de_exact::t_phase_sample(a, id, red, rand, od, ow, n, ctx->stream); HOOK_POST("phase_sample"); }
+int de_test_dir_sample(de_ctx *ctx, int kind, const float *nrm, float cmax, const uint32_t *rand, float *out, int n) { HOOK_PRE(false); de_exact::t_dir_sample(kind, nrm, cmax, rand, out, n, ctx->stream); HOOK_POST("dir_sample"); }
+int de_test_brdf(de_ctx *ctx, const float *al, const float *oc, const float *ba, const float *v, const float *nr, const float *l, float *out, int n) { HOOK_PRE(false); de_exact::t_brdf(al, oc, ba, v, nr, l, out, n, ctx->stream); HOOK_POST("brdf"); }
+int de_test_srgb2spec(de_ctx *ctx, const float *rgb, const float *wl, float *out, int n) { HOOK_PRE(true); de_exact::t_srgb2spec(ctx->scene, rgb, wl, out, n, ctx->stream); HOOK_POST("srgb2spec"); }
+int de_test_spectrum_sample(de_ctx *ctx, const uint32_t *rand, float *out, int n) { HOOK_PRE(true); de_exact::t_spectrum_sample(ctx->scene, rand, out, n, ctx->stream); HOOK_POST("spectrum_sample"); }
+int de_test_tex_fetch(de_ctx *ctx, int slot, const float *pos, float *out, int n) {
+    HOOK_PRE(true);
+    NEED(slot >= 0 && slot < DE_TEX_COUNT && ctx->have_tex[slot], "texture slot not uploaded");
+    de_exact::t_tex_fetch(ctx->scene, slot, pos, out, n, ctx->stream); HOOK_POST("tex_fetch");
+}
+int de_test_cast_dir(de_ctx *ctx, const float *u, const float *v, const uint32_t *rand, float *out, int n) { HOOK_PRE(true); de_exact::t_cast_dir(ctx->scene, u, v, rand, out, n, ctx->stream); HOOK_POST("cast_dir"); }
+int de_test_opendrt(de_ctx *ctx, const float *rgb, float *out, int n) { HOOK_PRE(false); de_exact::t_opendrt(rgb, out, n, ctx->stream); HOOK_POST("opendrt"); }
+int de_test_agx(de_ctx *ctx, const float *rgb, float *out, int n) { HOOK_PRE(false); de_exact::t_agx(rgb, out, n, ctx->stream); HOOK_POST("agx"); }
+int de_test_crf(de_ctx *ctx, const float *rgb, float *out, int n) { HOOK_PRE(true); de_exact::t_crf(ctx->scene, rgb, out, n, ctx->stream); HOOK_POST("crf"); }
+int de_test_srgb_oetf(de_ctx *ctx, const float *x, float *out, int n) { HOOK_PRE(false); de_exact::t_srgb_oetf(x, out, n, ctx->stream); HOOK_POST("srgb_oetf"); }
+int de_test_intersect_land(de_ctx *ctx, const float *pos, const float *dir, float *out, int n) { HOOK_PRE(true); de_exact::t_intersect_land(ctx->scene, pos, dir, out, n, ctx->stream); HOOK_POST("intersect_land"); }
+int de_test_land_normal(de_ctx *ctx, const float *pos, float *out, int n) { HOOK_PRE(true); de_exact::t_land_normal(ctx->scene, pos, out, n, ctx->stream); HOOK_POST("land_normal"); }
+int de_test_land_material(de_ctx *ctx, const float *pos, float *out, int n) { HOOK_PRE(true); de_exact::t_land_material(ctx->scene, pos, out, n, ctx->stream); HOOK_POST("land_material"); }
+int de_test_cloud_limits(de_ctx *ctx, const float *pos, const float *dir, const float *land, float *out, int n) { HOOK_PRE(false); de_exact::t_cloud_limits(pos, dir, land, out, n, ctx->stream); HOOK_POST("cloud_limits"); }
+int de_test_clouds_density(de_ctx *ctx, const float *pos, float *out, int n) { HOOK_PRE(true); de_exact::t_clouds_density(ctx->scene, pos, out, n, ctx->stream); HOOK_POST("clouds_density"); }
+int de_test_raymarch_T(de_ctx *ctx, const float *pos, const float *dir, const float *ext, float *out, int n) { HOOK_PRE(false); de_exact::t_raymarch_T(pos, dir, ext, out, n, ctx->stream); HOOK_POST("raymarch_T"); }
+int de_test_tracking(de_ctx *ctx, int kind, const float *pos, const float *dir, const float *land, const float *wl, uint32_t seed, float *out, int n) { HOOK_PRE(true); de_exact::t_tracking(ctx->scene, kind, pos, dir, land, wl, seed, out, n, ctx->stream); HOOK_POST("tracking"); }
+int de_test_trace_paths(de_ctx *ctx, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out, int n) {
+    ENTER();
+    if (n <= 0) return DE_OK;
+    int rc = ready_to_render(ctx);
+    if (rc) return rc;
+    de_exact::t_trace_paths(ctx->scene, px, py, sample, seed, out, n, ctx->stream);
+    HOOK_POST("trace_paths");
+}
+
+}  // extern "C"

@@ -1,0 +1,267 @@
+// de_kernels.cu -- kernels of one arithmetic flavour (compiled twice, see de_device.cuh):
+//   render (one thread per pixel), resolve, and -- in the parity build only -- the set-up kernels
+//   (derived scene parameters, per-wavelength table) and the unit-test hooks.
+#include "de_integrator.cuh"
+#include "de_launch.h"
+
+namespace DE_NS {
+
+#define LD3(p, i) f3((p)[3 * (i)], (p)[3 * (i) + 1], (p)[3 * (i) + 2])
+#define ST3(p, i, v) do { float3 _v = (v); (p)[3 * (i)] = _v.x; (p)[3 * (i) + 1] = _v.y; (p)[3 * (i) + 2] = _v.z; } while (0)
+
+// Renderer.render (renderer.py:283-330): one thread per pixel, a 16x8 film tile per 128-thread
+// CTA as in renderer.py:43-46,304; n_spp samples per launch instead of one.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_render_mega(DevScene s, float *__restrict__ accum, int n_spp, uint32_t seed, uint32_t first_sample,
+                                                    int x0, int y0, int w, int h) {
+    int tiles_x = (w + kDeTileW - 1) / kDeTileW;
+    int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    int px = x0 + tx * kDeTileW + (threadIdx.x & (kDeTileW - 1)), py = y0 + ty * kDeTileH + (threadIdx.x / kDeTileW);
+    if (px >= x0 + w || py >= y0 + h) return;
+    const DevDerived dv = *s.derived;
+    Counters cn;
+    cn.clear();
+    size_t k = ((size_t)py * s.W + px) * 3;
+    float3 acc = f3(accum[k], accum[k + 1], accum[k + 2]);
+    for (int sp = 0; sp < n_spp; ++sp) {
+        float3 c = render_sample<COUNT>(s, dv, px, py, first_sample + (uint32_t)sp, seed, cn, nullptr, nullptr);
+        acc = acc + c;
+    }
+    accum[k] = acc.x; accum[k + 1] = acc.y; accum[k + 2] = acc.z;
+    if (COUNT) cn.flush(s.counters);
+}
+void launch_render_mega(const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, bool count, cudaStream_t st) {
+    int tiles = ((w + kDeTileW - 1) / kDeTileW) * ((h + kDeTileH - 1) / kDeTileH);
+    if (count) k_render_mega<true><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
+    else k_render_mega<false><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
+}
+
+// Renderer._render_to_image (renderer.py:346-365)
+__global__ void __launch_bounds__(256) k_resolve(DevScene s, const float *__restrict__ accum, float *__restrict__ out, int spp) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.W * s.H) return;
+    int i = idx % s.W, j = idx / s.W;
+    OpenDrtPar op = opendrt_params();
+    AgxPar ap;
+    if (s.tonemapper == 1) ap = agx_params();
+    float3 o = resolve_pixel(s, op, ap, i, j, LD3(accum, (size_t)idx), spp);
+    ST3(out, (size_t)idx, o);
+}
+void launch_resolve(const DevScene &s, const float *accum, float *out, int spp, cudaStream_t st) {
+    int n = s.W * s.H;
+    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(s, accum, out, spp);
+}
+
+#if DE_EXACT
+// ------------------------------------------------------------------ set-up kernels
+// SceneParameters + camera basis (renderer.py:230,272-277,293-302; pathtracer.py:20)
+__global__ void k_prepare(DevScene s, DevDerived *out) {
+    DevDerived d;
+    float sun_radius = 6.95e8f, sun_distance = 1.4959e11f;
+    d.sun_angular_radius = sun_radius / sun_distance;
+    d.sun_cos_angle = cosf(d.sun_angular_radius);
+    float rx = -sinf(s.sun_path_rot), ry = cosf(s.sun_path_rot);
+    d.light_dir = f3(-sinf(s.sun_angle), cosf(s.sun_angle) * rx, cosf(s.sun_angle) * ry);
+    d.up_n = normalize(s.up);
+    d.cam_d = normalize(s.look_at - s.cam_pos);
+    d.cam_du = normalize(cross(d.cam_d, d.up_n));
+    d.cam_dv = normalize(cross(d.cam_du, d.cam_d));
+    d.normal_eps = (float)(3.141592653589793 * 6371e3 / (double)s.topo_tex_w);
+    *out = d;
+}
+void launch_prepare(const DevScene &s, DevDerived *out, cudaStream_t st) { k_prepare<<<1, 1, 0, st>>>(s, out); }
+
+// Everything that depends on the sampled wavelength only, for each reachable bisection midpoint
+// mid = j/512 (colour.py:12-48; pathtracer.py:332-343,355; colour.py:62-71).
+__global__ void k_build_lambda(DevScene s, LambdaRow *lam, float *cdf) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= kLambdaBins) return;
+    float mid = (float)j / 512.0f;
+    const float third = (float)(1.0 / 3.0);
+    float r = tex_f32(s.cie, 441, 2, 3, 0, mid, 0.25f), g = tex_f32(s.cie, 441, 2, 3, 1, mid, 0.25f), b = tex_f32(s.cie, 441, 2, 3, 2, mid, 0.25f);
+    cdf[j] = saturate((third * r + third * g) + third * b);
+    LambdaRow L;
+    float wl = 390.0f + 441.0f * mid;
+    L.wavelength = wl;
+    float3 resp = f3(tex_f32(s.cie, 441, 2, 3, 0, mid, 0.75f), tex_f32(s.cie, 441, 2, 3, 1, mid, 0.75f), tex_f32(s.cie, 441, 2, 3, 2, mid, 0.75f));
+    float3 mx = f3(tex_f32(s.cie, 441, 2, 3, 0, 1.0f, 0.25f), tex_f32(s.cie, 441, 2, 3, 1, 1.0f, 0.25f), tex_f32(s.cie, 441, 2, 3, 2, 1.0f, 0.25f));
+    float pdf = dot(resp, mx);
+    L.resp_x = resp.x; L.resp_y = resp.y; L.resp_z = resp.z;
+    L.rcp_pdf = (pdf > 1e-3f && !(isinf(pdf) || isnan(pdf))) ? 1.0f / pdf : 0.0f;
+    L.ext_r = spectra_extinction_rayleigh(wl);
+    L.ext_m = spectra_extinction_mie(wl);
+    L.ext_o = spectra_extinction_ozone(wl, s.o3);
+    float3 d0 = get_density(0.0f);
+    float o3max = get_ozone_density(25000.0f);
+    L.max_ext_rmo = (L.ext_r * d0.x + L.ext_m * d0.y) + L.ext_o * o3max;
+    L.sun_power = plancks(5778.0f, wl);
+    L.nightlights_power = plancks(2700.0f, wl) * 0.0001f;
+    float sun_angular_radius = 6.95e8f / 1.4959e11f;
+    L.sun_irradiance = L.sun_power * cone_angle_to_solid_angle(sun_angular_radius);
+    float3 c; bool valid;
+    srgb_to_spectrum_coeff(s.s2s, wl, c, valid);
+    L.s2s_r = c.x; L.s2s_g = c.y; L.s2s_b = c.z; L.s2s_valid = valid ? 1.0f : 0.0f;
+    lam[j] = L;
+}
+void launch_build_lambda(const DevScene &s, LambdaRow *lam, float *cdf, cudaStream_t st) { k_build_lambda<<<kLambdaBins / 128, 128, 0, st>>>(s, lam, cdf); }
+
+// ------------------------------------------------------------------ unit-test hooks
+#define HOOK_BEGIN(name, ...) __global__ void k_##name(int n, __VA_ARGS__) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+#define HOOK_END }
+#define HOOK_LAUNCH(name, n, st, ...) k_##name<<<((n) + 127) / 128, 128, 0, st>>>(n, __VA_ARGS__)
+
+HOOK_BEGIN(philox, const uint32_t *in6, uint32_t *out4)
+    Rng r; r.key0 = in6[6 * i + 4]; r.key1 = in6[6 * i + 5]; r.sample = in6[6 * i]; r.bounce = in6[6 * i + 1]; r.draw = in6[6 * i + 2] << 2;
+    // counter word 3 is fixed to 0 by the stream contract; the KAT with c3 != 0 is covered on the host oracle
+    r.refill(); out4[4 * i] = r.b0; out4[4 * i + 1] = r.b1; out4[4 * i + 2] = r.b2; out4[4 * i + 3] = r.b3;
+HOOK_END
+void t_philox(const uint32_t *in6, uint32_t *out4, int n, cudaStream_t st) { HOOK_LAUNCH(philox, n, st, in6, out4); }
+
+HOOK_BEGIN(rsi, const float *pos, const float *dir, const float *r, float *out)
+    float2 o = rsi(LD3(pos, i), LD3(dir, i), r[i]); out[2 * i] = o.x; out[2 * i + 1] = o.y;
+HOOK_END
+void t_rsi(const float *pos, const float *dir, const float *r, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(rsi, n, st, pos, dir, r, out); }
+
+HOOK_BEGIN(density, const float *h, float *out)
+    ST3(out, i, get_density(h[i]));
+HOOK_END
+void t_density(const float *h, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(density, n, st, h, out); }
+
+HOOK_BEGIN(spectra, DevScene s, const float *wl, float *out)
+    float w = wl[i];
+    out[5 * i] = spectra_extinction_rayleigh(w); out[5 * i + 1] = spectra_extinction_mie(w); out[5 * i + 2] = spectra_extinction_ozone(w, s.o3);
+    out[5 * i + 3] = plancks(5778.0f, w); out[5 * i + 4] = plancks(2700.0f, w);
+HOOK_END
+void t_spectra(const DevScene &s, const float *wl, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(spectra, n, st, s, wl, out); }
+
+HOOK_BEGIN(phase_eval, const float *a, const float *b, const int32_t *id, const int32_t *red, float *out)
+    out[i] = evaluate_phase(LD3(a, i), LD3(b, i), id[i], red[i] != 0);
+HOOK_END
+void t_phase_eval(const float *a, const float *b, const int32_t *id, const int32_t *red, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(phase_eval, n, st, a, b, id, red, out); }
+
+HOOK_BEGIN(phase_sample, const float *a, const int32_t *id, const int32_t *red, const uint32_t *rand, float *od, float *ow)
+    ListRng r{rand + 4 * i}; float w; float3 d = sample_phase(LD3(a, i), id[i], red[i] != 0, r, w); ST3(od, i, d); ow[i] = w;
+HOOK_END
+void t_phase_sample(const float *a, const int32_t *id, const int32_t *red, const uint32_t *rand, float *od, float *ow, int n, cudaStream_t st) { HOOK_LAUNCH(phase_sample, n, st, a, id, red, rand, od, ow); }
+
+HOOK_BEGIN(dir_sample, int kind, const float *nrm, float cmax, const uint32_t *rand, float *out)
+    ListRng r{rand + 2 * i};
+    float3 d = kind == 0 ? sample_cone_oriented(cmax, LD3(nrm, i), r) : sample_hemisphere_cosine_weighted(LD3(nrm, i), r);
+    ST3(out, i, d);
+HOOK_END
+void t_dir_sample(int kind, const float *nrm, float cmax, const uint32_t *rand, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(dir_sample, n, st, kind, nrm, cmax, rand, out); }
+
+HOOK_BEGIN(brdf, const float *al, const float *oc, const float *ba, const float *v, const float *nr, const float *l, float *out)
+    float ndl; out[2 * i] = earth_brdf(al[i], oc[i], ba[i], LD3(v, i), LD3(nr, i), LD3(l, i), ndl); out[2 * i + 1] = ndl;
+HOOK_END
+void t_brdf(const float *al, const float *oc, const float *ba, const float *v, const float *nr, const float *l, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(brdf, n, st, al, oc, ba, v, nr, l, out); }
+
+HOOK_BEGIN(srgb2spec, DevScene s, const float *rgb, const float *wl, float *out)
+    out[i] = srgb_to_spectrum(s.s2s, LD3(rgb, i), wl[i]);
+HOOK_END
+void t_srgb2spec(const DevScene &s, const float *rgb, const float *wl, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(srgb2spec, n, st, s, rgb, wl, out); }
+
+// literal LUT bisection AND the table path used by the integrators; both must agree (out[5..9] mirrors out[0..4])
+HOOK_BEGIN(spectrum_sample, DevScene s, const uint32_t *rand, float *out)
+    float xi = u32_to_unit(rand[i]); float wl, rcp, mid; float3 resp;
+    spectrum_sample(s.cie, xi, wl, resp, rcp, mid);
+    int bin = spectrum_bin(s.cdf, xi); LambdaRow L = s.lam[bin];
+    bool same = L.wavelength == wl && L.resp_x == resp.x && L.resp_y == resp.y && L.resp_z == resp.z && L.rcp_pdf == rcp;
+    out[5 * i] = same ? wl : -1.0f; out[5 * i + 1] = resp.x; out[5 * i + 2] = resp.y; out[5 * i + 3] = resp.z; out[5 * i + 4] = rcp;
+HOOK_END
+void t_spectrum_sample(const DevScene &s, const uint32_t *rand, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(spectrum_sample, n, st, s, rand, out); }
+
+HOOK_BEGIN(tex_fetch, DevScene s, int slot, const float *pos, float *out)
+    float3 p = LD3(pos, i); out[4 * i + 3] = 0.0f;
+    if (s.tex[slot].c == 1) { out[4 * i] = sample_sphere_r8(s.tex[slot], p); out[4 * i + 1] = 0.0f; out[4 * i + 2] = 0.0f; }
+    else { float3 c = sample_sphere_rgb8(s.tex[slot], p); out[4 * i] = c.x; out[4 * i + 1] = c.y; out[4 * i + 2] = c.z; }
+HOOK_END
+void t_tex_fetch(const DevScene &s, int slot, const float *pos, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(tex_fetch, n, st, s, slot, pos, out); }
+
+HOOK_BEGIN(cast_dir, DevScene s, const float *u, const float *v, const uint32_t *rand, float *out)
+    DevDerived dv = *s.derived;
+    ST3(out, i, get_cast_dir(s, dv, u[i], v[i], u32_to_unit(rand[2 * i]), u32_to_unit(rand[2 * i + 1])));
+HOOK_END
+void t_cast_dir(const DevScene &s, const float *u, const float *v, const uint32_t *rand, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(cast_dir, n, st, s, u, v, rand, out); }
+
+HOOK_BEGIN(opendrt, const float *rgb, float *out)
+    OpenDrtPar p = opendrt_params(); ST3(out, i, openDR_transform(LD3(rgb, i), p));
+HOOK_END
+void t_opendrt(const float *rgb, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(opendrt, n, st, rgb, out); }
+
+HOOK_BEGIN(agx, const float *rgb, float *out)
+    AgxPar p = agx_params(); ST3(out, i, agx_display_transform(LD3(rgb, i), p));
+HOOK_END
+void t_agx(const float *rgb, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(agx, n, st, rgb, out); }
+
+HOOK_BEGIN(crf, DevScene s, const float *rgb, float *out)
+    ST3(out, i, camera_response(s, LD3(rgb, i)));
+HOOK_END
+void t_crf(const DevScene &s, const float *rgb, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(crf, n, st, s, rgb, out); }
+
+HOOK_BEGIN(srgb_oetf, const float *x, float *out)
+    out[i] = srgb_transfer1(x[i]);
+HOOK_END
+void t_srgb_oetf(const float *x, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(srgb_oetf, n, st, x, out); }
+
+HOOK_BEGIN(intersect_land, DevScene s, const float *pos, const float *dir, float *out)
+    Counters cn; out[i] = intersect_land<false>(s, LD3(pos, i), LD3(dir, i), s.land_height_scale, cn);
+HOOK_END
+void t_intersect_land(const DevScene &s, const float *pos, const float *dir, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(intersect_land, n, st, s, pos, dir, out); }
+
+HOOK_BEGIN(land_normal, DevScene s, const float *pos, float *out)
+    Counters cn; DevDerived dv = *s.derived; ST3(out, i, land_normal<false>(s, dv.normal_eps, LD3(pos, i), s.land_height_scale, cn));
+HOOK_END
+void t_land_normal(const DevScene &s, const float *pos, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(land_normal, n, st, s, pos, out); }
+
+HOOK_BEGIN(land_material, DevScene s, const float *pos, float *out)
+    Counters cn; LandMaterial m = get_land_material<false>(s, LD3(pos, i), cn);
+    ST3(out, 2 * i, m.albedo_srgb); out[6 * i + 3] = m.ocean; out[6 * i + 4] = m.bathymetry; out[6 * i + 5] = m.emissive;
+HOOK_END
+void t_land_material(const DevScene &s, const float *pos, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(land_material, n, st, s, pos, out); }
+
+HOOK_BEGIN(cloud_limits, const float *pos, const float *dir, const float *land, float *out)
+    float a, b; intersect_cloud_limits(LD3(pos, i), LD3(dir, i), land[i], a, b); out[2 * i] = a; out[2 * i + 1] = b;
+HOOK_END
+void t_cloud_limits(const float *pos, const float *dir, const float *land, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(cloud_limits, n, st, pos, dir, land, out); }
+
+HOOK_BEGIN(clouds_density, DevScene s, const float *pos, float *out)
+    Counters cn; out[i] = get_clouds_density<false>(s, LD3(pos, i), cn);
+HOOK_END
+void t_clouds_density(const DevScene &s, const float *pos, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(clouds_density, n, st, s, pos, out); }
+
+// pathtracer.py:471-500
+HOOK_BEGIN(raymarch_T, const float *pos_, const float *dir_, const float *ext_, float *out)
+    float3 pos = LD3(pos_, i), dir = LD3(dir_, i), ext = LD3(ext_, i);
+    const int steps = 16; float r_steps = 1.0f / (float)steps, T = 0.0f;
+    bool visibility = rsi(pos, dir, kPlanetR).y > 0.0f;
+    if (!visibility) {
+        float2 atm = rsi(pos, dir, kAtmosUpper);
+        float t_max = atm.y; if (atm.y < 0.0f) t_max = -1.0f;
+        float dd = t_max * r_steps; float3 step = dir * dd, od = f3(0, 0, 0);
+        for (int k = 0; k < steps; ++k) { float3 d = get_density(get_elevation(pos)); od = od + d * dd; pos = pos + step; }
+        T = expf(-dot(ext, od));
+    }
+    out[i] = T;
+HOOK_END
+void t_raymarch_T(const float *pos, const float *dir, const float *ext, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(raymarch_T, n, st, pos, dir, ext, out); }
+
+HOOK_BEGIN(tracking, DevScene s, int kind, const float *pos, const float *dir, const float *land, const float *wl, uint32_t seed, float *out)
+    Counters cn; Rng r; r.init(seed, (uint32_t)i, 0u); r.set_bounce(1u);
+    float3 ext = f3(spectra_extinction_rayleigh(wl[i]), spectra_extinction_mie(wl[i]), spectra_extinction_ozone(wl[i], s.o3));
+    float3 d0 = get_density(0.0f); float o3max = get_ozone_density(25000.0f);
+    float mr = (ext.x * d0.x + ext.y * d0.y) + ext.z * o3max, mc = kCloudsExtinct * kCloudsDensity;
+    if (kind == 0) { float t; int id; int ev = sample_interaction<false>(s, LD3(pos, i), LD3(dir, i), land[i], ext, kCloudsExtinct, mr, mc, r, cn, t, id); out[3 * i] = (float)ev; out[3 * i + 1] = t; out[3 * i + 2] = (float)id; }
+    else { out[3 * i] = sample_transmittance<false>(s, LD3(pos, i), LD3(dir, i), land[i], ext, kCloudsExtinct, mr, mc, r, cn); out[3 * i + 1] = 0.0f; out[3 * i + 2] = 0.0f; }
+HOOK_END
+void t_tracking(const DevScene &s, int kind, const float *pos, const float *dir, const float *land, const float *wl, uint32_t seed, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(tracking, n, st, s, kind, pos, dir, land, wl, seed, out); }
+
+HOOK_BEGIN(trace_paths, DevScene s, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out)
+    Counters cn; DevDerived dv = *s.derived; float wl, L;
+    float3 c = render_sample<false>(s, dv, px[i], py[i], sample[i], seed, cn, &wl, &L);
+    out[5 * i] = c.x; out[5 * i + 1] = c.y; out[5 * i + 2] = c.z; out[5 * i + 3] = wl; out[5 * i + 4] = L;
+HOOK_END
+void t_trace_paths(const DevScene &s, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(trace_paths, n, st, s, px, py, sample, seed, out); }
+#endif  // DE_EXACT
+
+}  // namespace DE_NS

@@ -1,0 +1,259 @@
+"""`Renderer` -- the reference's host driver class (renderer.py:16-401) on top of libde.so.
+
+Same construction, attributes, setters, 0-d "fields" (`renderer.fov[None]` ...), `copy_textures`,
+`reset_framebuffer`, `accumulate`, `fetch_image`.  Device memory is owned by torch tensors or by
+the libde context and is only ever handed across the C-ABI as raw pointers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, textures as _tex
+
+
+class _Field0:
+    """Taichi 0-d field look-alike: `f[None]` reads, `f[None] = v` writes (renderer.py:27-41)."""
+
+    def __init__(self, owner, value, kind="f32"):
+        self._owner, self._kind = owner, kind
+        self._v = None
+        self._set(value)
+
+    def _set(self, v):
+        if self._kind == "f32":
+            self._v = float(np.float32(v))
+        elif self._kind == "i32":
+            self._v = int(v)
+        else:
+            self._v = tuple(float(np.float32(x)) for x in v)
+
+    def __getitem__(self, key):
+        assert key is None, "0-d field: index with [None]"
+        return self._v
+
+    def __setitem__(self, key, value):
+        assert key is None, "0-d field: index with [None]"
+        self._set(value)
+        self._owner._dirty = True
+
+
+class _CudaView:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": "<f4", "version": 2, "strides": None}
+
+
+class Renderer:
+    def __init__(self, image_res, up, textures=None, device=None, mode="wavefront", texture_quality=_tex.TEXTURE_QUALITY,
+                 texture_dir="textures", assets_dir=None, seed=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.DeError("no CUDA device: the B200 renderer has no CPU fallback")
+        self._torch = torch
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.image_res = (int(image_res[0]), int(image_res[1]))
+        if self.image_res[0] % 16 or self.image_res[1] % 8:
+            raise ValueError("image_res must be a multiple of (16, 8) (renderer.py:46)")
+        self.aspect_ratio = image_res[0] / image_res[1]
+        self.vignette_strength = 0.9   # renderer.py:20-22
+        self.vignette_radius = 0.0
+        self.vignette_center = [0.5, 0.5]
+        self.current_spp = 0
+        self.seed = int(seed)
+        self.tonemapper = 0            # 0 OpenDRT (renderer.py:357), 1 AgX (renderer.py:356, commented out upstream)
+        self._dirty = True
+        self._ctx = C.c_void_p()
+        rc = self._lib.de_create(C.byref(self._ctx), self.device.index, self.image_res[0], self.image_res[1])
+        if rc != 0:
+            raise _lib.DeError("de_create failed (%d)" % rc)
+        self.set_mode(mode)
+
+        # 0-d fields (renderer.py:27-41) with the defaults of renderer.py:49-56
+        self.camera_pos = _Field0(self, (-15000000.0, 0.0, 15000000.0), "vec3")  # earth_viewer.py:27
+        self.look_at = _Field0(self, (0.0, 0.0, 0.0), "vec3")
+        self.up = _Field0(self, (0.0, 1.0, 0.0), "vec3")
+        self.fov = _Field0(self, 0.0)
+        self.aspect_scale = _Field0(self, 1.0)
+        self.exposure = _Field0(self, 2.5)
+        self.gamma = _Field0(self, 1.0)
+        self.selected_crf = _Field0(self, 0, "i32")
+        self.crf_count = _Field0(self, 0, "i32")
+        self.sun_angle = _Field0(self, 0.0)
+        self.sun_path_rot = _Field0(self, 0.0)
+        self.set_up(*up)
+        self.set_fov(np.radians(27.0) * 0.5)
+        self.set_aspect_scale(1.0)
+        self.set_exposure(2.5)
+        self.set_gamma(1.0)
+        self.set_crf(0)
+        self.set_sun_angle(np.radians(60.0))
+        self.set_sun_path_rot(np.radians(-45.0))
+        self.land_height_scale = 7800.0  # renderer.py:58
+
+        # textures (renderer.py:60-94): dict of arrays, a directory of the NASA maps, or None -> texture_dir
+        if textures is None or isinstance(textures, str):
+            textures = _tex.load_directory(textures or texture_dir, texture_quality)
+        self._textures = {k: np.ascontiguousarray(textures[k], dtype=np.uint8) for k in _lib.TEX_SLOTS}
+        self.topography_tex_res = self._textures["topography"].shape[1::-1]
+
+        # LUTs + camera response functions (renderer.py:96-134,147-167)
+        luts = _tex.load_luts(assets_dir)
+        self._luts = luts
+        self.crf_names = list(luts["crf_names"])
+        self.crf_lut_res = (1024, len(self.crf_names))
+        self.set_crf_count(self.crf_lut_res[1])
+        self._textures_copied = False
+        self._image = torch.empty((self.image_res[1], self.image_res[0], 3), dtype=torch.float32, device=self.device)
+        ptr = C.c_void_p()
+        self._check(self._lib.de_get_accum(self._ctx, C.byref(ptr)))
+        self._accum = torch.as_tensor(_CudaView(ptr.value, (self.image_res[1], self.image_res[0], 3)), device=self.device)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        _lib.check(self._ctx, rc)
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.de_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_mode(self, mode):
+        """'wavefront' (product), 'megakernel' (1 thread/pixel baseline) or 'parity' (IEEE source-order)."""
+        self.mode = mode
+        self._check(self._lib.de_set_mode(self._ctx, _lib.MODES[mode]))
+
+    def set_counting(self, enabled):
+        self._check(self._lib.de_set_counting(self._ctx, int(bool(enabled))))
+
+    def counters(self):
+        c = _lib.DeCounters()
+        self._check(self._lib.de_get_counters(self._ctx, C.byref(c)))
+        return c.as_dict()
+
+    def _bind_stream(self):
+        self._check(self._lib.de_set_stream(self._ctx, C.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def _params(self):
+        p = _lib.DeParams()
+        p.cam_pos[:] = self.camera_pos[None]
+        p.look_at[:] = self.look_at[None]
+        p.up[:] = self.up[None]
+        p.fov, p.aspect_scale = self.fov[None], self.aspect_scale[None]
+        p.sun_angle, p.sun_path_rot = self.sun_angle[None], self.sun_path_rot[None]
+        p.land_height_scale = self.land_height_scale
+        p.exposure, p.gamma = self.exposure[None], self.gamma[None]
+        p.selected_crf, p.crf_count = self.selected_crf[None], self.crf_count[None]
+        p.vignette_strength, p.vignette_radius = self.vignette_strength, self.vignette_radius
+        p.vignette_center[:] = self.vignette_center
+        p.tonemapper = int(self.tonemapper)
+        p.topo_tex_w = int(self.topography_tex_res[0])
+        return p
+
+    def _push_params(self):
+        p = self._params()
+        key = bytes(p)
+        if self._dirty or key != getattr(self, "_pushed", None):
+            self._check(self._lib.de_set_params(self._ctx, C.byref(p)))
+            self._pushed, self._dirty = key, False
+
+    # ------------------------------------------------------------------ reference surface
+    def copy_textures(self):
+        """renderer.py:136-145: host arrays -> device textures + LUTs."""
+        self._bind_stream()
+        for i, name in enumerate(_lib.TEX_SLOTS):
+            t = self._textures[name]
+            ch = 1 if t.ndim == 2 else t.shape[2]
+            self._check(self._lib.de_upload_texture(self._ctx, i, t.ctypes.data_as(C.c_void_p), t.shape[1], t.shape[0], ch))
+        L = self._luts
+        cie = np.ascontiguousarray(L["cie"], np.float32)
+        s2s = np.ascontiguousarray(L["srgb2spec"], np.float16)
+        o3 = np.ascontiguousarray(L["o3"], np.float32)
+        crf = np.ascontiguousarray(L["crf"], np.float32)
+        self._check(self._lib.de_upload_luts(self._ctx, cie.ctypes.data_as(C.c_void_p), s2s.ctypes.data_as(C.c_void_p),
+                                             o3.ctypes.data_as(C.c_void_p), crf.ctypes.data_as(C.c_void_p), crf.shape[0]))
+        self._textures_copied = True
+
+    def load_crfs(self, directory=None):
+        """renderer.py:147-167; returns (1024, n, 3) like the reference.  directory=None -> packaged curves."""
+        if directory is not None:
+            crf, names = _tex.load_crf_directory(directory)
+            self._luts = dict(self._luts, crf=crf, crf_names=names)
+            self.crf_names = list(names)
+            self.crf_lut_res = (1024, len(names))
+            self.set_crf_count(len(names))
+            self._textures_copied = False
+        return np.ascontiguousarray(self._luts["crf"].transpose(1, 0, 2))
+
+    def set_camera_pos(self, x, y, z): self.camera_pos[None] = (x, y, z)          # renderer.py:224
+    def set_up(self, x, y, z): self.up[None] = (x, y, z)                          # :228 (normalised on device)
+    def set_look_at(self, x, y, z): self.look_at[None] = (x, y, z)                # :232
+    def set_fov(self, fov): self.fov[None] = fov                                  # :236
+    def set_aspect_scale(self, scale): self.aspect_scale[None] = scale            # :240
+    def set_exposure(self, exposure): self.exposure[None] = exposure              # :244
+    def set_gamma(self, gam): self.gamma[None] = gam                              # :248
+    def set_crf(self, index): self.selected_crf[None] = index                     # :252
+    def set_crf_count(self, num): self.crf_count[None] = num                      # :256
+    def set_sun_angle(self, ang): self.sun_angle[None] = ang                      # :260
+    def set_sun_path_rot(self, ang): self.sun_path_rot[None] = ang                # :264
+
+    def apply_config(self, cfg):
+        """Apply a parsed 10-line config (config.load_config)."""
+        self.set_camera_pos(*cfg["cam_pos"]); self.set_look_at(*cfg["look_at"]); self.set_up(*cfg["up"])
+        self.set_fov(cfg["fov"]); self.set_aspect_scale(cfg["aspect_scale"]); self.set_exposure(cfg["exposure"])
+        self.set_crf(cfg["selected_crf"]); self.set_gamma(cfg["gamma"])
+        self.set_sun_angle(cfg["sun_angle"]); self.set_sun_path_rot(cfg["sun_path_rot"])
+
+    def reset_framebuffer(self):
+        """renderer.py:367-369"""
+        self._bind_stream()
+        self.current_spp = 0
+        self._check(self._lib.de_reset(self._ctx))
+
+    def accumulate(self, n_spp=1, window=None, first_sample=None):
+        """renderer.py:371-380 (+1 spp); n_spp > 1 renders several samples per pixel in one launch.
+        first_sample: Philox sample index of the first sample (default: current_spp)."""
+        if not self._textures_copied:
+            self.copy_textures()
+        self._bind_stream()
+        self._push_params()
+        x0, y0, w, h = window or (0, 0, self.image_res[0], self.image_res[1])
+        fs = self.current_spp if first_sample is None else int(first_sample)
+        self._check(self._lib.de_accumulate(self._ctx, int(n_spp), self.seed & 0xFFFFFFFF, fs & 0xFFFFFFFF, x0, y0, w, h))
+        self.current_spp += int(n_spp)
+
+    def fetch_image(self, accum=None, spp=None):
+        """renderer.py:382-384: resolve + tonemap; returns a (W, H, 3) float32 CUDA tensor in [0,1]
+        indexed [x][y] with y up, like the reference's `_rendered_image` field."""
+        if not self._textures_copied:
+            self.copy_textures()
+        self._bind_stream()
+        self._push_params()
+        spp = self.current_spp if spp is None else int(spp)
+        src = C.c_void_p(accum.data_ptr()) if accum is not None else None
+        self._check(self._lib.de_resolve(self._ctx, src, C.c_void_p(self._image.data_ptr()), max(spp, 1)))
+        return self._image.permute(1, 0, 2)
+
+    @property
+    def color_buffer(self):
+        """The accumulation buffer (renderer.py:25) as a [H][W][3] float32 CUDA tensor (linear sRGB sums)."""
+        return self._accum
+
+    def sync(self):
+        self._check(self._lib.de_sync(self._ctx))
+
+    def render(self, spp, batch=None):
+        """Convenience: reset + accumulate `spp` samples (in batches) + fetch_image."""
+        self.reset_framebuffer()
+        batch = batch or spp
+        done = 0
+        while done < spp:
+            n = min(batch, spp - done)
+            self.accumulate(n)
+            done += n
+        return self.fetch_image()

@@ -1,0 +1,159 @@
+/* de_api.h -- C-ABI of libde.so: the B200-native drop-in for the Taichi kernels of
+ * AntonioFerreras/Digital-Earth (renderer.py / pathtracer.py).
+ *
+ * The reference has no FFI: its seam is the Python class `Renderer` (renderer.py:16) whose
+ * methods launch two Taichi kernels.  Every entry point below names the reference interface it
+ * replaces (file:line relative to the reference root).  Plain pointers and sizes only; no torch
+ * or CUDA types in any signature (streams and device pointers travel as void* / float*).
+ * INTEGRATION.md shows the ctypes binding a maintainer adds to renderer.py.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a negative DE_ERR_* code; de_last_error() has the text;
+ *     nothing throws across the ABI.
+ *   - one ctx <-> one CUDA device <-> one stream.  Calls enqueue work asynchronously on the ctx
+ *     stream (de_set_stream shares torch's current stream); de_sync() or a sync of that stream
+ *     completes them.  A ctx is not thread-safe; different ctxs may be driven concurrently.
+ *   - images / accumulation buffers are row-major [y][x][3] float32, y = 0 is the BOTTOM row
+ *     (reference pixel (u,v)=(0,0) is bottom-left, renderer.py:269-279).  The reference's
+ *     16x8 film tiling (renderer.py:43-46) is an internal scheduling detail here.
+ *   - textures are uint8 row-major [y][x][c], y = 0 is v = 0 (south pole); i.e. the transpose of
+ *     the reference's ti.tools.imread arrays ([x][y][c], y up; renderer.py:61-94).
+ *   - RNG: Philox4x32-10, key = (seed, y*W + x), counter = (sample_index, bounce, draw>>2, 0);
+ *     bounce 0 = camera/wavelength draws, bounce k+1 = path segment k.
+ */
+#ifndef DE_API_H
+#define DE_API_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* libde.so is built with -fvisibility=hidden */
+#endif
+
+#define DE_ABI_VERSION 1
+
+enum {
+    DE_OK = 0,
+    DE_ERR_INVALID = -1, /* bad argument (NULL, size, W%16 / H%8, slot ...) */
+    DE_ERR_CUDA = -2,    /* a CUDA runtime call failed                      */
+    DE_ERR_STATE = -3,   /* call order: textures / LUTs / params missing    */
+    DE_ERR_NOMEM = -4
+};
+
+/* texture slots: renderer.py:61-94 */
+enum { DE_TEX_ALBEDO = 0, DE_TEX_TOPOGRAPHY, DE_TEX_OCEAN, DE_TEX_CLOUDS, DE_TEX_BATHYMETRY, DE_TEX_EMISSIVE, DE_TEX_STARS, DE_TEX_COUNT };
+
+/* integrator flavours */
+enum {
+    DE_MODE_WAVEFRONT = 0, /* product path: persistent-thread, stage-sorted, FMA + fast intrinsics */
+    DE_MODE_MEGAKERNEL = 1,/* one thread per pixel, same fast arithmetic (baseline for profiles)   */
+    DE_MODE_PARITY = 2     /* one thread per pixel, IEEE source-order arithmetic (no FMA
+                              contraction, accurate libm): comparable to the oracle per path       */
+};
+
+typedef struct de_ctx de_ctx;
+
+/* Scalar state of the reference Renderer: the 0-d Taichi fields written by the set_* kernels
+ * (renderer.py:224-266), SceneParameters inputs (lib/parameters.py:10-15, renderer.py:293-302)
+ * and the Python attributes read by _render_to_image (renderer.py:20-22,58). */
+typedef struct DeParams {
+    float cam_pos[3];        /* set_camera_pos                      renderer.py:224 */
+    float look_at[3];        /* set_look_at                         renderer.py:232 */
+    float up[3];             /* set_up (normalised on device)       renderer.py:228 */
+    float fov;               /* tangent half-height                 renderer.py:236 */
+    float aspect_scale;      /*                                     renderer.py:240 */
+    float sun_angle;         /* radians                             renderer.py:260 */
+    float sun_path_rot;      /* radians                             renderer.py:264 */
+    float land_height_scale; /* 7800                                renderer.py:58  */
+    float exposure;          /* stops                               renderer.py:244 */
+    float gamma;             /*                                     renderer.py:248 */
+    int32_t selected_crf;    /*                                     renderer.py:252 */
+    int32_t crf_count;       /*                                     renderer.py:256 */
+    float vignette_strength; /* 0.9                                 renderer.py:20  */
+    float vignette_radius;   /* 0.0                                 renderer.py:21  */
+    float vignette_center[2];/* (0.5, 0.5)                          renderer.py:22  */
+    int32_t tonemapper;      /* 0 = OpenDRT (renderer.py:357), 1 = AgX (renderer.py:356) */
+    int32_t topo_tex_w;      /* TOPOGRAPHY_TEX_RES[0] (lib/textures.py) used at pathtracer.py:20;
+                                0 = width of the uploaded topography texture */
+} DeParams;
+
+/* event counters of the last de_accumulate (for the roofline's FLOP/path formula) */
+typedef struct DeCounters {
+    uint64_t paths, segments, rmo_steps, cloud_steps, sdf_evals, tex_fetches, surface_hits, rng_draws;
+} DeCounters;
+
+int de_abi_version(void);
+
+/* Renderer.__init__(image_res, up)  renderer.py:17-58.  W%16==0 and H%8==0 as renderer.py:46. */
+int de_create(de_ctx **out, int device, int width, int height);
+void de_destroy(de_ctx *ctx);
+const char *de_last_error(de_ctx *ctx);
+int de_set_stream(de_ctx *ctx, void *cuda_stream);
+int de_set_mode(de_ctx *ctx, int mode);
+
+/* the eleven set_* kernels + direct field writes  renderer.py:224-266, earth_viewer.py:308-314 */
+int de_set_params(de_ctx *ctx, const DeParams *p);
+
+/* texture load + copy_*_texture kernels  renderer.py:61-94,136-143,170-210 (host pointer) */
+int de_upload_texture(de_ctx *ctx, int slot, const uint8_t *host_texels, int w, int h, int channels);
+/* LUT load + copy_CIE_LUT_texture / copy_CRF_LUT_texture  renderer.py:97-134,144-145,212-222
+ *   cie [2][441][3] f32 (LUT/CIE.dat), srgb2spec [300][3] fp16 bits, o3 [441] f32, crf [n_crf][1024][3] f32 */
+int de_upload_luts(de_ctx *ctx, const float *cie, const uint16_t *srgb2spec_f16, const float *o3, const float *crf, int n_crf);
+
+/* Renderer.reset_framebuffer  renderer.py:367-369 */
+int de_reset(de_ctx *ctx);
+/* Renderer.accumulate == Renderer.render kernel  renderer.py:283-330,371-380, generalised:
+ * n_spp samples per pixel with sample indices [first_sample, first_sample+n_spp) over the pixel
+ * window [x0,x0+w) x [y0,y0+h) (whole frame: 0,0,W,H).  Adds into the ctx accumulation buffer. */
+int de_accumulate(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h);
+/* device pointer of the accumulation buffer ([H][W][3] f32 linear sRGB sums; color_buffer,
+ * renderer.py:25,330) so the caller can view it as a tensor / hand it to NCCL */
+int de_get_accum(de_ctx *ctx, float **dev_ptr);
+/* Renderer.fetch_image == _render_to_image kernel  renderer.py:346-365,382-384.
+ * dev_out: device [H][W][3] f32 in [0,1].  accum_override (device, may be NULL) resolves another
+ * buffer of the same shape, e.g. an NCCL-reduced one. */
+int de_resolve(de_ctx *ctx, const float *accum_override, float *dev_out, int spp_total);
+/* convenience for non-torch callers: resolve + copy to host memory, synchronous */
+int de_fetch_image_host(de_ctx *ctx, float *host_out, int spp_total);
+int de_sync(de_ctx *ctx);
+int de_get_counters(de_ctx *ctx, DeCounters *out); /* synchronises */
+int de_set_counting(de_ctx *ctx, int enabled);     /* counters cost atomics: off by default */
+
+/* ---- test hooks: the deterministic sub-paths of SURVEY 8(a), DEVICE pointers, n items --------
+ * Each evaluates the IEEE source-order (parity) flavour of one reference function. */
+int de_test_philox(de_ctx *, const uint32_t *ctr4_key2, uint32_t *out4, int n);
+int de_test_rsi(de_ctx *, const float *pos3, const float *dir3, const float *r, float *out2, int n);        /* math_utils.py:17 */
+int de_test_density(de_ctx *, const float *h, float *out3, int n);                                           /* volume_rendering_models.py:270 */
+int de_test_spectra(de_ctx *, const float *wavelength, float *out5, int n);                                  /* :194-224, colour.py:51 */
+int de_test_phase_eval(de_ctx *, const float *ray3, const float *light3, const int32_t *id, const int32_t *reduce, float *out, int n); /* pathtracer.py:235 */
+int de_test_phase_sample(de_ctx *, const float *ray3, const int32_t *id, const int32_t *reduce, const uint32_t *rand4, float *out_dir3, float *out_w, int n); /* pathtracer.py:249 */
+int de_test_dir_sample(de_ctx *, int kind, const float *n3, float cos_max, const uint32_t *rand2, float *out3, int n); /* sampling.py:25,30 */
+int de_test_brdf(de_ctx *, const float *albedo, const float *ocean, const float *bathy, const float *v3, const float *n3, const float *l3, float *out2, int n); /* surface_rendering_models.py:9 */
+int de_test_srgb2spec(de_ctx *, const float *rgb3, const float *wavelength, float *out, int n);              /* colour.py:62 */
+int de_test_spectrum_sample(de_ctx *, const uint32_t *rand, float *out5, int n);                             /* colour.py:12 */
+int de_test_tex_fetch(de_ctx *, int slot, const float *pos3, float *out4, int n);                            /* math_utils.py:38 */
+int de_test_cast_dir(de_ctx *, const float *u, const float *v, const uint32_t *rand2, float *out3, int n);   /* renderer.py:269 */
+int de_test_opendrt(de_ctx *, const float *rgb3, float *out3, int n);                                        /* OpenDRT.py:221 */
+int de_test_agx(de_ctx *, const float *rgb3, float *out3, int n);                                            /* AgX.py:131 */
+int de_test_crf(de_ctx *, const float *rgb3, float *out3, int n);                                            /* renderer.py:333 */
+int de_test_srgb_oetf(de_ctx *, const float *x, float *out, int n);                                          /* colour.py:74 */
+int de_test_intersect_land(de_ctx *, const float *pos3, const float *dir3, float *out, int n);               /* pathtracer.py:27 */
+int de_test_land_normal(de_ctx *, const float *pos3, float *out3, int n);                                    /* pathtracer.py:16 */
+int de_test_land_material(de_ctx *, const float *pos3, float *out6, int n);                                  /* pathtracer.py:284 */
+int de_test_cloud_limits(de_ctx *, const float *pos3, const float *dir3, const float *land, float *out2, int n); /* pathtracer.py:145 */
+int de_test_clouds_density(de_ctx *, const float *pos3, float *out, int n);                                  /* pathtracer.py:48 */
+int de_test_raymarch_T(de_ctx *, const float *pos3, const float *dir3, const float *ext3, float *out, int n);/* pathtracer.py:471 */
+/* kind 0: sample_interaction -> (event, t, id); kind 1: sample_transmittance -> (T, 0, 0); Philox key (seed, i), bounce 1 */
+int de_test_tracking(de_ctx *, int kind, const float *pos3, const float *dir3, const float *land, const float *wavelength, uint32_t seed, float *out3, int n); /* pathtracer.py:172,211 */
+/* individual path samples in PARITY arithmetic: out5 = rgb contribution, wavelength, radiance   renderer.py:305-330 */
+int de_test_trace_paths(de_ctx *, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out5, int n);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* DE_API_H */
