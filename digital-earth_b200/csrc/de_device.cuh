@@ -75,13 +75,19 @@ DE_DEV float pow_ti(float x, float y) { return y == 2.0f ? x * x : powf(x, y); }
 DE_DEV float log2_ti(float x) { return logf(x) / 0.6931471805599453f; }  // taichi.math.log2
 
 // ---------------------------------------------------------------- Philox4x32-10 stream
+// RNG contract (include/de_api.h): slot i of (pixel, sample, bounce) = word i&3 of
+// Philox4x32-10(key=(seed,pixel), ctr=(sample,bounce,i>>2,0)); align() / skip() implement the two
+// consumption rules (consumers start on a block boundary; a ratio-tracking trip owns two slots).
 struct Rng {
     uint32_t key0, key1, sample, bounce, draw;
     uint32_t b0, b1, b2, b3;
+    bool valid;
     DE_DEV void init(uint32_t seed, uint32_t pixel, uint32_t sample_index) {
-        key0 = seed; key1 = pixel; sample = sample_index; bounce = 0; draw = 0;
+        key0 = seed; key1 = pixel; sample = sample_index; bounce = 0; draw = 0; valid = false;
     }
-    DE_DEV void set_bounce(uint32_t b) { bounce = b; draw = 0; }
+    DE_DEV void set_bounce(uint32_t b) { bounce = b; draw = 0; valid = false; }
+    DE_DEV void align() { draw = (draw + 3u) & ~3u; valid = false; }
+    DE_DEV void skip() { draw += 1u; valid = false; }
     DE_DEV void refill() {
         uint32_t c0 = sample, c1 = bounce, c2 = draw >> 2, c3 = 0u, k0 = key0, k1 = key1;
 #pragma unroll
@@ -92,10 +98,11 @@ struct Rng {
             k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
         }
         b0 = c0; b1 = c1; b2 = c2; b3 = c3;
+        valid = true;
     }
     DE_DEV uint32_t next_u32() {
         uint32_t lane = draw & 3u;
-        if (lane == 0u) refill();
+        if (lane == 0u || !valid) refill();
         ++draw;
         return lane == 0u ? b0 : (lane == 1u ? b1 : (lane == 2u ? b2 : b3));
     }
@@ -105,6 +112,8 @@ struct Rng {
 struct ListRng {  // explicit draws for the unit-test hooks
     const uint32_t *p;
     DE_DEV float next() { return (float)((*p++) >> 8) * (1.0f / 16777216.0f); }
+    DE_DEV void align() {}
+    DE_DEV void skip() {}
 };
 DE_DEV float u32_to_unit(uint32_t v) { return (float)(v >> 8) * (1.0f / 16777216.0f); }
 

@@ -71,6 +71,7 @@ DE_DEV int delta_tracking(const DevScene &s, float3 pos, float3 dir, float t_sta
     float t = t_start;
     pos = pos + dir * t;
     int id = 0, event = kNullEvent;
+    rng.align();
     while (t < t_max) {
         float t_step = -logf(rng.next()) / max_ext;
         pos = pos + dir * t_step;
@@ -112,8 +113,10 @@ DE_DEV float ratio_tracking(const DevScene &s, float3 pos, float3 dir, float t_s
     float t = t_start;
     pos = pos + dir * t;
     float T = 1.0f;
+    rng.align();
     while (t < t_max) {
         float t_step = -logf(rng.next()) / max_ext;
+        rng.skip();
         pos = pos + dir * t_step;
         t += t_step;
         if (t >= t_max) break;
@@ -194,6 +197,7 @@ DE_DEV float path_tracer(const DevScene &s, const DevDerived &dv, const LambdaRo
         float interaction_dist; int id;
         int event = sample_interaction<COUNT>(s, ray_pos, ray_dir, earth_isect, ext_rmo, ext_cloud, max_ext_rmo, max_ext_cloud, rng, cn, interaction_dist, id);
         if (scatter_count > 9 && id == kCloud) id = kIsoCloud;
+        rng.align();
         float3 light_dir = sample_cone_oriented(dv.sun_cos_angle, dv.light_dir, rng);
         if (event == kAbsorbEvent) break;
         else if (event == kScatterEvent) {
@@ -204,6 +208,7 @@ DE_DEV float path_tracer(const DevScene &s, const DevDerived &dv, const LambdaRo
             float direct_phase = evaluate_phase(ray_dir, light_dir, id, scatter_count > 0);
             in_scattering += throughput * direct_T * lr.sun_irradiance * direct_phase;
             float pdp;
+            rng.align();
             float3 sd = sample_phase(ray_dir, id, scatter_count > 0, rng, pdp);
             ray_dir = sd; ray_pos = ipos; throughput *= pdp;
         } else if (earth_isect > 0.0f) {
@@ -220,6 +225,7 @@ DE_DEV float path_tracer(const DevScene &s, const DevDerived &dv, const LambdaRo
             float dbrdf = earth_brdf(albedo, m.ocean, m.bathymetry, -ray_dir, nrm, light_dir, ndl);
             in_scattering += throughput * direct_T * (vis ? 1.0f : 0.0f) * lr.sun_irradiance * dbrdf * ndl;
             float3 view_dir = -ray_dir;
+            rng.align();
             ray_dir = sample_hemisphere_cosine_weighted(nrm, rng);
             ray_pos = offset_pos;
             float unused;

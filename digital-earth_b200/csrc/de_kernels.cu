@@ -111,7 +111,7 @@ void launch_build_lambda(const DevScene &s, LambdaRow *lam, float *cdf, cudaStre
 #define HOOK_LAUNCH(name, n, st, ...) k_##name<<<((n) + 127) / 128, 128, 0, st>>>(n, __VA_ARGS__)
 
 HOOK_BEGIN(philox, const uint32_t *in6, uint32_t *out4)
-    Rng r; r.key0 = in6[6 * i + 4]; r.key1 = in6[6 * i + 5]; r.sample = in6[6 * i]; r.bounce = in6[6 * i + 1]; r.draw = in6[6 * i + 2] << 2;
+    Rng r; r.init(in6[6 * i + 4], in6[6 * i + 5], in6[6 * i]); r.bounce = in6[6 * i + 1]; r.draw = in6[6 * i + 2] << 2;
     // counter word 3 is fixed to 0 by the stream contract; the KAT with c3 != 0 is covered on the host oracle
     r.refill(); out4[4 * i] = r.b0; out4[4 * i + 1] = r.b1; out4[4 * i + 2] = r.b2; out4[4 * i + 3] = r.b3;
 HOOK_END

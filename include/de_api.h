@@ -18,8 +18,13 @@
  *     16x8 film tiling (renderer.py:43-46) is an internal scheduling detail here.
  *   - textures are uint8 row-major [y][x][c], y = 0 is v = 0 (south pole); i.e. the transpose of
  *     the reference's ti.tools.imread arrays ([x][y][c], y up; renderer.py:61-94).
- *   - RNG: Philox4x32-10, key = (seed, y*W + x), counter = (sample_index, bounce, draw>>2, 0);
- *     bounce 0 = camera/wavelength draws, bounce k+1 = path segment k.
+ *   - RNG: per (pixel, sample, bounce) a stream of 32-bit slots; slot i = word i&3 of
+ *     Philox4x32-10(key = (seed, y*W + x), counter = (sample_index, bounce, i>>2, 0)); bounce 0 =
+ *     wavelength + pixel jitter, bounce k+1 = path segment k.  Each ti.random() of the reference
+ *     takes the next slot; tracking passes, the light-direction sample, sample_phase and the
+ *     hemisphere sample start on a multiple of 4, and a ratio-tracking trip owns two slots (see
+ *     oracle/de_oracle.c header).  Every integrator flavour consumes the same stream, so a pixel's
+ *     samples are the same paths in all of them.
  */
 #ifndef DE_API_H
 #define DE_API_H

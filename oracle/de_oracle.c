@@ -22,8 +22,19 @@
  * constant; max/min = fmaxf/fminf; float->int casts truncate; bilinear fetch =
  * manual FP32 lerp a+f*(b-a), x then y, texel centres (i+.5)/N, clamp-to-edge;
  * the CIE LUT is rounded to fp16 before filtering (rgba16f texture,
- * renderer.py:97); xi = (u32>>8)*2^-24; RNG = Philox4x32-10 with
- * key=(seed,pixel) counter=(sample,bounce,draw>>2,0).
+ * renderer.py:97); xi = (u32>>8)*2^-24.
+ *
+ * RNG contract (shared by oracle, golden generator, and every CUDA integrator flavour):
+ * per (pixel, sample, bounce) a stream of 32-bit SLOTS; slot i is word i&3 of
+ * Philox4x32-10(key=(seed,pixel), counter=(sample,bounce,i>>2,0)); bounce 0 = wavelength +
+ * pixel jitter, bounce k+1 = path segment k.  Each ti.random() of the reference takes the next
+ * slot, with two rules that make the stream SIMT-friendly (one Philox block per two tracking
+ * steps, no per-lane phase):
+ *   (1) the slot index is rounded up to a multiple of 4 on entry to
+ *       sample_interaction_delta_tracking, transmittance_ratio_tracking, the light-direction
+ *       sample_cone_oriented, sample_phase and sample_hemisphere_cosine_weighted;
+ *   (2) every loop trip of transmittance_ratio_tracking owns two slots (the second is unused),
+ *       exactly like a delta-tracking trip (free flight + acceptance test).
  */
 #include <math.h>
 #include <pthread.h>
@@ -72,6 +83,7 @@ typedef struct {
     uint32_t buf[4];
     const uint32_t *list; /* explicit draw list (unit tests) when non-NULL */
     uint32_t list_pos;
+    int buf_valid;
     orc_counters *cnt;
 } orc_rng;
 
@@ -90,15 +102,19 @@ static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 static uint32_t rng_u32(orc_rng *r) {
     if (r->cnt) r->cnt->rng_draws++;
     if (r->list) return r->list[r->list_pos++];
-    if ((r->draw & 3u) == 0) {
+    if ((r->draw & 3u) == 0 || !r->buf_valid) {
         uint32_t ctr[4] = { r->sample, r->bounce, r->draw >> 2, 0u }, key[2] = { r->key0, r->key1 };
         philox4x32_10(ctr, key, r->buf);
+        r->buf_valid = 1;
     }
     return r->buf[(r->draw++) & 3u];
 }
+/* contract rule (1) / (2); no-ops for the explicit draw lists of the unit-test entry points */
+static void rng_align(orc_rng *r) { if (!r->list) { r->draw = (r->draw + 3u) & ~3u; r->buf_valid = 0; } }
+static void rng_skip(orc_rng *r) { if (!r->list) { r->draw += 1u; r->buf_valid = 0; } }
 /* ti.random(f32) */
 static float rnd(orc_rng *r) { return (float)(rng_u32(r) >> 8) * (1.0f / 16777216.0f); }
-static void rng_bounce(orc_rng *r, uint32_t b) { r->bounce = b; r->draw = 0; }
+static void rng_bounce(orc_rng *r, uint32_t b) { r->bounce = b; r->draw = 0; r->buf_valid = 0; }
 
 /* ------------------------------------------------------------ vector ops -- */
 static inline v3 V3(float x, float y, float z) { v3 r = { x, y, z }; return r; }
@@ -638,6 +654,7 @@ static int delta_tracking(const orc_scene *s, v3 pos, v3 dir, float t_start, flo
     float t = t_start;
     pos = add3(pos, scl3(dir, t));
     int id = 0, event = NULL_EVENT;
+    rng_align(r);
     while (t < t_max) {
         float t_step = -logf(rnd(r)) / max_ext;
         pos = add3(pos, scl3(dir, t_step));
@@ -668,8 +685,10 @@ static float ratio_tracking(const orc_scene *s, v3 pos, v3 dir, float t_start, f
     float t = t_start;
     pos = add3(pos, scl3(dir, t));
     float T = 1.0f;
+    rng_align(r);
     while (t < t_max) {
         float t_step = -logf(rnd(r)) / max_ext;
+        rng_skip(r);
         pos = add3(pos, scl3(dir, t_step));
         t += t_step;
         if (t >= t_max) break;
@@ -762,6 +781,7 @@ static float path_tracer(const orc_scene *s, const scene_params *sc, float wavel
         float interaction_dist; int id;
         int event = sample_interaction(s, ray_pos, ray_dir, earth_isect, ext, max_ext_rmo, max_ext_cloud, r, cnt, &interaction_dist, &id);
         if (scatter_count > 9 && id == CLOUD_ID) id = ISOTROPIC_CLOUD_ID;
+        rng_align(r);
         v3 light_dir = sample_cone_oriented(sc->sun_cos_angle, sc->light_direction, r);
         if (event == ABSORB_EVENT) break;
         else if (event == SCATTER_EVENT) {
@@ -773,6 +793,7 @@ static float path_tracer(const orc_scene *s, const scene_params *sc, float wavel
             float direct_phase = evaluate_phase(ray_dir, light_dir, id, scatter_count > 0);
             in_scattering += throughput * direct_T * sun_irradiance * direct_phase;
             float pdp;
+            rng_align(r);
             v3 sd = sample_phase(ray_dir, id, scatter_count > 0, r, &pdp);
             ray_dir = sd; ray_pos = ipos; throughput *= pdp;
         } else if (earth_isect > 0.0f) {
@@ -789,6 +810,7 @@ static float path_tracer(const orc_scene *s, const scene_params *sc, float wavel
             float dbrdf = earth_brdf(albedo, m.ocean, m.bathymetry, neg3(ray_dir), nrm, light_dir, &ndl);
             in_scattering += throughput * direct_T * (float)vis * sun_irradiance * dbrdf * ndl;
             v3 view_dir = neg3(ray_dir);
+            rng_align(r);
             ray_dir = sample_hemisphere_cosine_weighted(nrm, r);
             ray_pos = offset_pos;
             float unused;

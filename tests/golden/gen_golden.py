@@ -20,7 +20,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 REF = os.environ.get("DE_REFERENCE", "/root/reference")
 sys.path.insert(0, os.path.join(ROOT, "oracle", "ti_shim"))
 sys.path.insert(0, REF)
-sys.path.insert(0, os.path.join(ROOT, "digital-earth_b200"))
 
 import taichi as ti  # noqa: E402  (the shim)
 from taichi.math import vec2, vec3, vec4  # noqa: E402
@@ -34,7 +33,11 @@ import lib.sampling as sampling  # noqa: E402
 import lib.OpenDRT as odrt  # noqa: E402
 import lib.AgX as agx  # noqa: E402
 from lib.parameters import PathParameters, SceneParameters  # noqa: E402
-import synth  # noqa: E402
+import importlib.util as _ilu  # noqa: E402
+
+_spec = _ilu.spec_from_file_location("de_synth", os.path.join(ROOT, "digital-earth_b200", "synth.py"))
+synth = _ilu.module_from_spec(_spec)
+_spec.loader.exec_module(synth)
 
 f32 = np.float32
 TEX_W, TEX_H = 64, 32
@@ -55,21 +58,51 @@ def philox4x32_10(ctr, key):
 
 
 class Stream:
-    """key=(seed,pixel) counter=(sample,bounce,draw>>2,0) -- the framework's RNG contract."""
+    """The framework's RNG contract (oracle/de_oracle.c header): slot i of (pixel, sample, bounce) is
+    word i&3 of Philox4x32-10(key=(seed,pixel), counter=(sample,bounce,i>>2,0)); consumers listed in
+    ALIGNED start on a multiple of 4; a ratio-tracking trip owns two slots."""
 
     def __init__(self, seed, pixel, sample):
         self.key = (seed & 0xFFFFFFFF, pixel & 0xFFFFFFFF)
-        self.sample, self.bounce, self.draw, self.buf = sample, 0, 0, None
+        self.sample, self.bounce, self.draw, self.stride = sample, 0, 0, 1
 
     def set_bounce(self, b):
         self.bounce, self.draw = b, 0
 
+    def align(self):
+        self.draw = (self.draw + 3) & ~3
+
     def __call__(self):
-        if self.draw & 3 == 0:
-            self.buf = philox4x32_10((self.sample, self.bounce, self.draw >> 2, 0), self.key)
-        v = self.buf[self.draw & 3]
-        self.draw += 1
+        v = philox4x32_10((self.sample, self.bounce, self.draw >> 2, 0), self.key)[self.draw & 3]
+        self.draw += self.stride
         return v
+
+
+ALIGNED = ("sample_interaction_delta_tracking", "transmittance_ratio_tracking", "sample_cone_oriented", "sample_phase",
+           "sample_hemisphere_cosine_weighted")
+
+
+def install_contract_hooks(cur):
+    """Wrap the reference functions named in the contract (module globals of pathtracer.py, resolved at
+    call time) so the random source is aligned / strided as the contract says.  cur["s"] = live Stream."""
+    saved = {}
+    for name in ALIGNED:
+        orig = getattr(pt, name)
+        saved[name] = orig
+
+        def wrapped(*a, _orig=orig, _ratio=(name == "transmittance_ratio_tracking"), **k):
+            s_ = cur.get("s")
+            if isinstance(s_, Stream):
+                s_.align()
+                if _ratio:
+                    s_.stride = 2
+            try:
+                return _orig(*a, **k)
+            finally:
+                if isinstance(s_, Stream):
+                    s_.stride = 1
+        setattr(pt, name, wrapped)
+    return saved
 
 
 class ListStream:
@@ -347,20 +380,21 @@ def main():
     G["trk_pos"], G["trk_dir"], G["trk_land"], G["trk_wl"], G["trk_seed"] = tp, td, tl, tw, np.uint32(99)
     d0 = volume.get_density(f32(0.0)); o3m = volume.get_ozone_density(f32(25000.0))
     si, st = [], []
+    cur = {}
+    saved = install_contract_hooks(cur)
     for i in range(n):
         ext = vec4(volume.spectra_extinction_rayleigh(f32(tw[i])), volume.spectra_extinction_mie(f32(tw[i])),
                    volume.spectra_extinction_ozone(f32(tw[i]), R.O3_crossec_LUT_buff), f32(volume.clouds_extinct))
         mr = (ext.xyz * vec3(d0.x, d0.y, o3m)).sum(); mc = ext.w * f32(volume.clouds_density)  # pathtracer.py:355-356
-        s_ = Stream(99, i, 0); s_.set_bounce(1); ti._set_random_source(s_)
+        s_ = Stream(99, i, 0); s_.set_bounce(1); ti._set_random_source(s_); cur["s"] = s_
         ev, t_, id_ = pt.sample_interaction(V(tp[i]), V(td[i]), f32(tl[i]), ext, mr, mc, T["clouds"])
         si.append([float(ev), float(t_), float(id_)])
-        s_ = Stream(99, i, 0); s_.set_bounce(1); ti._set_random_source(s_)
+        s_ = Stream(99, i, 0); s_.set_bounce(1); ti._set_random_source(s_); cur["s"] = s_
         st.append([float(pt.sample_transmittance(V(tp[i]), V(td[i]), f32(tl[i]), ext, mr, mc, T["clouds"])), 0.0, 0.0])
     G["trk_interaction_out"], G["trk_transmittance_out"] = np.array(si, np.float32), np.array(st, np.float32)
 
     # ---- full path samples: Renderer.render body (renderer.py:305-330) on the three configs
     orig_si = pt.sample_interaction
-    cur = {}
 
     def hooked(*a, **k):  # one call per path segment (pathtracer.py:362) -> advance the bounce key
         cur["s"].set_bounce(cur["s"].bounce + 1)
@@ -393,6 +427,8 @@ def main():
             G["cfg_%s_%s" % (key, k2)] = np.array(cfg[k2], np.float64)
         G["cfg_%s_scalars" % key] = np.array([cfg[k2] for k2 in ("fov", "aspect_scale", "exposure", "selected_crf", "gamma", "sun_angle", "sun_path_rot")], np.float64)
     pt.sample_interaction = orig_si
+    for name, fn in saved.items():
+        setattr(pt, name, fn)
     G["path_seed"] = np.uint32(5)
     G["img_res"] = np.array([IMG_W, IMG_H], np.int32)
     # Random123 known-answer vectors for Philox4x32-10
