@@ -188,7 +188,7 @@ int de_upload_texture(de_ctx *ctx, int slot, const uint8_t *host, int w, int h, 
     cudaTextureDesc td{};
     td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
     td.filterMode = cudaFilterModePoint;
-    td.readMode = cudaReadModeElementType;
+    td.readMode = cudaReadModeNormalizedFloat;  // unorm8 -> [0,1] in the TEX unit
     td.normalizedCoords = 0;
     CU(cudaCreateTextureObject(&t.obj, &rd, &td, nullptr));
     t.data = ctx->d_tex[slot]; t.w = w; t.h = h; t.c = channels;

@@ -158,12 +158,41 @@ DE_DEV float unorm8(uint8_t t) {
     return (float)t * (1.0f / 255.0f);
 #endif
 }
+#if !DE_EXACT
+// Product flavour: the 2x2 footprint comes from ONE texture instruction (tex2Dgather on the
+// block-linear copy, unorm8 -> float in the TEX unit); the weights stay ours (manual FP32 lerp,
+// as the oracle defines the filter).  The gather is addressed at the footprint's centre corner
+// (i0+1, j0+1), so texel selection never depends on the unit's fixed-point rounding, and the
+// clamp address mode reproduces the clamped indices at the borders.
+DE_DEV float tex_r8_gather(const DevTex &t, float u, float v) {
+    float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
+    float x0f = floorf(x), y0f = floorf(y);
+    float fx = x - x0f, fy = y - y0f;
+    float4 g = tex2Dgather<float4>(t.obj, x0f + 1.0f, y0f + 1.0f, 0);  // (x,y,z,w) = t01, t11, t10, t00
+    return lerp2(g.w, g.z, g.x, g.y, fx, fy);
+}
+DE_DEV float3 tex_rgb8_gather(const DevTex &t, float u, float v) {
+    float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
+    float x0f = floorf(x), y0f = floorf(y);
+    float fx = x - x0f, fy = y - y0f;
+    float4 r = tex2Dgather<float4>(t.obj, x0f + 1.0f, y0f + 1.0f, 0);
+    float4 g = tex2Dgather<float4>(t.obj, x0f + 1.0f, y0f + 1.0f, 1);
+    float4 b = tex2Dgather<float4>(t.obj, x0f + 1.0f, y0f + 1.0f, 2);
+    return f3(lerp2(r.w, r.z, r.x, r.y, fx, fy), lerp2(g.w, g.z, g.x, g.y, fx, fy), lerp2(b.w, b.z, b.x, b.y, fx, fy));
+}
+#endif
 DE_DEV float tex_r8(const DevTex &t, float u, float v) {
+#if !DE_EXACT
+    if (t.obj) return tex_r8_gather(t, u, v);
+#endif
     Bilin b = bilin_setup(t.w, t.h, u, v);
     const uint8_t *r0 = t.data + (size_t)b.y0 * t.w, *r1 = t.data + (size_t)b.y1 * t.w;
     return lerp2(unorm8(__ldg(r0 + b.x0)), unorm8(__ldg(r0 + b.x1)), unorm8(__ldg(r1 + b.x0)), unorm8(__ldg(r1 + b.x1)), b.fx, b.fy);
 }
 DE_DEV float3 tex_rgb8(const DevTex &t, float u, float v) {
+#if !DE_EXACT
+    if (t.obj) return tex_rgb8_gather(t, u, v);
+#endif
     Bilin b = bilin_setup(t.w, t.h, u, v);
     const uint8_t *p00 = t.data + ((size_t)b.y0 * t.w + b.x0) * 3, *p10 = t.data + ((size_t)b.y0 * t.w + b.x1) * 3;
     const uint8_t *p01 = t.data + ((size_t)b.y1 * t.w + b.x0) * 3, *p11 = t.data + ((size_t)b.y1 * t.w + b.x1) * 3;
@@ -173,9 +202,49 @@ DE_DEV float3 tex_rgb8(const DevTex &t, float u, float v) {
     o.z = lerp2(unorm8(__ldg(p00 + 2)), unorm8(__ldg(p10 + 2)), unorm8(__ldg(p01 + 2)), unorm8(__ldg(p11 + 2)), b.fx, b.fy);
     return o;
 }
+#if !DE_EXACT
+// Product flavour of atan2 / asin for the equirect mapping: minimax atan(a) = a*P(a^2) on [0,1]
+// (max error 3.2e-7 rad) and Abramowitz-Stegun 4.4.46 for asin (2.2e-8 rad); the libdevice
+// versions were 18.6 % of all issued instructions (profiles/r1_wavefront.md).  3e-7 rad is
+// 0.001 texel on a 21600-wide map.
+DE_DEV float fast_atan2(float y, float x) {
+    float ax = fabsf(x), ay = fabsf(y);
+    float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float a = __fdividef(mn, fmaxf(mx, 1e-30f));
+    float s = a * a;
+    float p = 0.006811773870140314f;
+    p = fmaf(p, s, -0.03360416740179062f);
+    p = fmaf(p, s, 0.07962362468242645f);
+    p = fmaf(p, s, -0.1323333978652954f);
+    p = fmaf(p, s, 0.19807815551757812f);
+    p = fmaf(p, s, -0.3331736922264099f);
+    p = fmaf(p, s, 0.9999961256980896f);
+    float r = p * a;
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = x < 0.0f ? 3.14159265358979324f - r : r;
+    return copysignf(r, y);
+}
+DE_DEV float fast_asin(float x) {
+    float ax = fminf(fabsf(x), 1.0f);
+    float p = -0.0012624911f;
+    p = fmaf(p, ax, 0.0066700901f);
+    p = fmaf(p, ax, -0.0170881256f);
+    p = fmaf(p, ax, 0.0308918810f);
+    p = fmaf(p, ax, -0.0501743046f);
+    p = fmaf(p, ax, 0.0889789874f);
+    p = fmaf(p, ax, -0.2145988016f);
+    p = fmaf(p, ax, 1.5707963050f);
+    float r = 1.57079632679489662f - sqrtf(1.0f - ax) * p;
+    return copysignf(r, x);
+}
+#endif
 // math_utils.py:25-28
 DE_DEV float2 sphere_UV_map(float3 n) {
+#if DE_EXACT
     return make_float2((atan2f(n.z, -n.x) / kPi + 1.0f) / 2.0f, asinf(n.y) / kPi + 0.5f);
+#else
+    return make_float2(fmaf(fast_atan2(n.z, -n.x), 0.5f / kPi, 0.5f), fmaf(fast_asin(n.y), 1.0f / kPi, 0.5f));
+#endif
 }
 // math_utils.py:38-44 (uv -> fract(uv))
 DE_DEV float2 sphere_uv(float3 pos) {
