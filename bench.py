@@ -1,0 +1,274 @@
+"""bench.py -- headline benchmark: spectral path samples/s and ms/frame at 1080p.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): `config - Apollo 11.txt` full-disk view, 1920x1080, 1024 spp,
+seeded synthetic 8192x4096 textures (the NASA maps are not available offline).  One STEP = one full
+frame = W*H*spp path samples through the product (wavefront) integrator.
+
+  value   : path samples/s, inputs resident in HBM, device time of K steps (CUDA events, max over ranks)
+  e2e     : the same metric through the reference-facing API with host buffers: per step the scene
+            parameters come from the host config (H2D), the frame is rendered, resolved/tonemapped and
+            copied back into pinned host memory (D2H), like one Renderer.accumulate()*spp + fetch_image()
+  roofline: FP32/SFU issue roofline of the render kernel (this path is neither HBM- nor
+            tensor-bound): algorithmic FLOP/path from the event counters x paths / kernel time against
+            148 SM x 128 lanes x 2 x sm_max_clock; `traffic` = DRAM bytes/launch from ncu if captured
+  cpu_baseline : the CPU oracle (a port of the reference's Taichi code, oracle/de_oracle.c) on all host
+            cores on a bounded sample (the same view at 480x272, 8 spp)
+N > 1: the frame's samples are sliced across ranks (rank r renders sample indices [r*spp/N, (r+1)*spp/N)
+of every pixel: perfectly balanced, the union is the 1-GPU sample set) and the float accumulation
+buffers are sum-reduced to rank 0 with NCCL inside the timed region; total work is fixed -> "strong".
+--impl reference: the reference itself needs Taichi (absent); its CPU implementation is therefore the
+oracle port, timed on all host threads on the bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+CFG_DIR = os.path.join(ROOT, "digital-earth_b200", "assets", "configs")
+SCENES = {"apollo": "Apollo 11", "florida": "florida", "sunset": "sunset hurricane"}
+METRIC, UNIT = "spectral_path_samples_per_sec_1080p", "path samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="apollo", choices=list(SCENES))
+    ap.add_argument("--res", default="1920x1080")
+    ap.add_argument("--spp", type=int, default=1024)
+    ap.add_argument("--tex", default="8192x4096")
+    ap.add_argument("--mode", default="wavefront", choices=["wavefront", "megakernel", "parity"])
+    ap.add_argument("--cpu-res", default="480x272")
+    ap.add_argument("--cpu-spp", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def flop_per_path(c):
+    """60*N_rmo + 45*N_cloud + 45*N_sdf + 400*N_seg + 200 (minimal necessary work)."""
+    p = max(c["paths"], 1)
+    return 60.0 * c["rmo_steps"] / p + 45.0 * c["cloud_steps"] / p + 45.0 * c["sdf_evals"] / p + 400.0 * c["segments"] / p + 200.0
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def scene_cfg(a):
+    import digital_earth_b200 as de
+    return de.load_config(os.path.join(CFG_DIR, "config - %s.txt" % SCENES[a.scene]))
+
+
+def textures_for(a, tw, th):
+    import digital_earth_b200 as de
+    return de.textures.synthetic(tw, th, cloud_cover=0.8 if a.scene == "sunset" else 0.5, hurricane=a.scene == "sunset", seed=0)
+
+
+def cpu_baseline(a, steps=1, textures=None):
+    """Oracle port on all host cores, bounded sample of the same view; returns (paths/s, description, cores)."""
+    from oracle import oracle as orc
+    cfg = scene_cfg(a)
+    cw, ch = map(int, a.cpu_res.split("x"))
+    tw, th = map(int, a.tex.split("x"))
+    tex = textures if textures is not None else textures_for(a, tw, th)
+    s = orc.Scene(tex, cw, ch, cam_pos=cfg["cam_pos"], look_at=cfg["look_at"], up=cfg["up"], fov=cfg["fov"], aspect_scale=cfg["aspect_scale"],
+                  sun_angle=cfg["sun_angle"], sun_path_rot=cfg["sun_path_rot"])
+    cores = os.cpu_count() or 1
+    times = []
+    for k in range(steps):
+        t0 = time.perf_counter()
+        orc.render(s, a.cpu_spp, first_sample=k * a.cpu_spp, nthreads=cores)
+        times.append(time.perf_counter() - t0)
+    paths = cw * ch * a.cpu_spp
+    sample = "%s view at %dx%d, %d spp (%d paths/step), %dx%d synthetic textures" % (SCENES[a.scene], cw, ch, a.cpu_spp, paths, tw, th)
+    return paths, times, sample, cores, tex
+
+
+def run_reference(a):
+    """--impl reference: CPU implementation of the path (oracle port; Taichi is not installable here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    paths, _, sample, cores, tex = cpu_baseline(a, steps=0)
+    _, wt, _, _, _ = cpu_baseline(a, steps=max(a.warmup, 0), textures=tex) if a.warmup else (0, [], 0, 0, 0)
+    _, times, _, _, _ = cpu_baseline(a, steps=a.steps, textures=tex)
+    total = sum(times)
+    v = paths * a.steps / total
+    W, H = map(int, a.res.split("x"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "%s, %dx%d, %d spp, synthetic %s textures" % (SCENES[a.scene], W, H, a.spp, a.tex), "scene": a.scene,
+                   "note": "CPU arm renders a bounded sample of this workload per step: " + sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    import torch
+    import torch.distributed as dist
+    import digital_earth_b200 as de
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, H = map(int, a.res.split("x"))
+    tw, th = map(int, a.tex.split("x"))
+    assert a.spp % world == 0, "spp must divide by the number of GPUs"
+    spp_local = a.spp // world
+    first = rank * spp_local
+
+    tex = textures_for(a, tw, th)
+    cfg = scene_cfg(a)
+    r = de.Renderer((W, H), (0, 1, 0), textures=tex, device=local, mode=a.mode)
+    r.apply_config(cfg)
+    r.copy_textures()
+    host_img = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(e2e):
+        flush.fill_(1)  # evict L2 between timed iterations (textures alone are 416 MB > L2 as well)
+        if e2e:
+            r.apply_config(cfg)   # host -> device: scene parameters for this frame
+        r.reset_framebuffer()
+        r.accumulate(spp_local, first_sample=first)
+        if world > 1:
+            dist.reduce(r.color_buffer, dst=0, op=dist.ReduceOp.SUM)  # NCCL over NVLink: the path's one exchange step
+        if e2e and rank == 0:
+            img = r.fetch_image(spp=a.spp)
+            host_img.copy_(img.permute(1, 0, 2), non_blocking=True)  # device -> pinned host ([H][W][3] storage order)
+
+    def timed(e2e, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # event counters -> algorithmic FLOP/path (outside the timed region, reduced spp)
+    r.set_counting(True)
+    r.reset_framebuffer(); r.accumulate(4, first_sample=first)
+    counters = r.counters()
+    r.set_counting(False)
+
+    for _ in range(max(a.warmup, 0)):
+        step(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(False, a.steps)
+    sampler.stop_flag = True
+    # kernel-only duration of the dominant kernel (render), measured live on its stream
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r.reset_framebuffer()
+    k0.record(); r.accumulate(spp_local, first_sample=first); k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1)
+    step(True)
+    ms_e2e = timed(True, a.steps)
+
+    paths_step = W * H * a.spp
+    value = paths_step * a.steps / (ms * 1e-3)
+    e2e_value = paths_step * a.steps / (ms_e2e * 1e-3)
+    clocks = sampler.summary()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+        fpp = flop_per_path(counters)
+        peak_tflops = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # FP32 FMA issue peak
+        achieved = fpp * (W * H * spp_local) / (kernel_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = prof.get("%s_%s_%d" % (a.scene, a.res, a.spp))
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s (config - %s.txt), %dx%d, %d spp, synthetic %dx%d textures" % (a.scene, SCENES[a.scene], W, H, a.spp, tw, th),
+                       "scene": a.scene, "integrator": a.mode, "ms_per_frame": ms / a.steps, "ms_per_spp": ms / a.steps / a.spp,
+                       "partition": "spp-slice x%d + ncclReduce(sum) of the f32 accumulation buffer" % world if world > 1 else "single GPU",
+                       "l2": "256 MiB flush between steps; textures (416 MB) exceed the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": 96, "d2h_bytes_per_step": W * H * 3 * 4},
+            "gpu_launches": a.steps * 1,  # one k_render_wavefront launch per step (memsets and the NCCL reduce are not ours)
+            "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                         "traffic": traffic, "kernel": "k_render_wavefront", "kernel_ms": kernel_ms, "flop_per_path": fpp,
+                         "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (max SM clock of MEASURED_PEAKS.json); HBM/tensor peaks do not bound this path" % sm_max,
+                         "events_per_path": {k: counters[k] / max(counters["paths"], 1) for k in ("segments", "rmo_steps", "cloud_steps", "sdf_evals", "tex_fetches", "surface_hits")}},
+            "clocks": clocks,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            paths, times, sample, cores, _ = cpu_baseline(a, steps=1, textures=tex)
+            line["cpu_baseline"] = {"value": paths / times[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
