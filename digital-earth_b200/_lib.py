@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libde.so")
+LIB_PATH = os.environ.get("DE_LIB_PATH") or os.path.join(_HERE, "libde.so")  # DE_LIB_PATH: tuning builds
 
 DE_MODE_WAVEFRONT, DE_MODE_MEGAKERNEL, DE_MODE_PARITY = 0, 1, 2
 MODES = {"wavefront": DE_MODE_WAVEFRONT, "megakernel": DE_MODE_MEGAKERNEL, "parity": DE_MODE_PARITY}

@@ -15,13 +15,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libde.so")
+OUT = os.path.join(HERE, "libde%s.so" % os.environ.get("DE_LIB_SUFFIX", ""))
+WF_DEFS = os.environ.get("DE_WF_DEFS", "").split()  # tuning sweeps: -DWF_WARPS=.. -DWF_SLOTS=..
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + ARCH
 UNITS = [
     ("de_kernels.cu", "de_kernels_exact.o", ["-DDE_EXACT=1", "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]),
     ("de_kernels.cu", "de_kernels_fast.o", ["-DDE_EXACT=0", "-use_fast_math"]),
-    ("de_wavefront.cu", "de_wavefront.o", ["-DDE_EXACT=0", "-use_fast_math"]),
+    ("de_wavefront.cu", "de_wavefront%s.o" % os.environ.get("DE_LIB_SUFFIX", ""), ["-DDE_EXACT=0", "-use_fast_math"] + WF_DEFS),
     ("de_api.cu", "de_api.o", []),
 ]
 

@@ -4,41 +4,46 @@
 // active per issued instruction -- path length and stage mix diverge, memory does not matter
 // (L1 97 %, L2 98 % hits, DRAM idle).  This kernel keeps every lane of a warp inside the SAME
 // inner loop:
-//   * each warp owns a pool of WF_N path states in shared memory (SoA, ~112 B per path), so
-//     state never touches HBM;
-//   * a path is a small state machine  SDF -> RMO -> CLOUD -> EVENT -> (SDF) -> RMO -> CLOUD ->
-//     NEE_DONE -> SDF ...  (pathtracer.py:349-453 cut at its loop boundaries);
-//   * the warp repeatedly ballots the pool, picks the most populated stage and runs a burst of
-//     that stage's loop body with all lanes converged; a lane whose path leaves the stage takes
-//     over a spare pool member of the same stage (warp-ballot compaction);
-//   * terminated paths are replaced at once from a global atomic work counter (path
-//     regeneration), 32 consecutive pixels of one 16x8 film tile and one sample index at a time.
-// The random stream of a path is the one the parity kernel uses (Philox key (seed,pixel), counter
-// (sample,bounce,draw)), so a pixel's samples are the same paths in every integrator flavour.
+//   * one persistent CTA per SM owns a pool of WF_SLOTS path states in shared memory (SoA,
+//     108 B per path), so path state never touches HBM;
+//   * a path is a small state machine  SDF -> SDF_DONE -> RMO -> RMO_DONE -> CLOUD -> EVENT ->
+//     (SDF ->) RMO -> CLOUD -> NEE_DONE -> SDF ...  (pathtracer.py:349-453 cut at its loop
+//     boundaries); every stage has a ring queue of ready slots in shared memory;
+//   * a warp pops up to 32 slots of the fullest queue and runs that stage with all lanes converged:
+//     loop stages (SDF / RMO / CLOUD) in bursts, refilling idle lanes from the same queue, the
+//     transition and shading stages as one-shot bodies; a finished lane only records its result
+//     and pushes the slot to the next stage's queue (warp-aggregated where the stage is one-shot);
+//   * terminated paths free their slot; free slots are refilled 32 at a time from a global atomic
+//     work counter (path regeneration): 32 neighbouring pixels of one 16x8 film tile, one sample.
+// The random stream of a path is the contract of include/de_api.h (Philox key (seed,pixel), counter
+// (sample,bounce,slot>>2)), so a pixel's samples are the same paths in every integrator flavour.
 #include "de_integrator.cuh"
 #include "de_launch.h"
 #include "de_wavefront.h"
 
 namespace de_fast {
 
-#ifndef WF_N
-#define WF_N 96        // pool slots per warp
+#ifndef WF_SLOTS
+#define WF_SLOTS 1792  // path states per CTA (one CTA per SM): 189 KB of state + 32 KB of queues
 #endif
 #ifndef WF_WARPS
-#define WF_WARPS 16    // warps per CTA, one persistent CTA per SM
+#define WF_WARPS 32
 #endif
 #ifndef WF_BURST
 #define WF_BURST 64    // max loop iterations per burst
 #endif
 #ifndef WF_MIN_ACTIVE
-#define WF_MIN_ACTIVE 16
+#define WF_MIN_ACTIVE 20  // a burst ends when fewer lanes than this are busy and the queue is dry
 #endif
+#ifndef WF_REFILL_MIN
+#define WF_REFILL_MIN 6  // idle lanes that trigger a mid-burst refill
+#endif
+constexpr int WF_RING = 2048;  // ring capacity per stage queue (power of two >= WF_SLOTS)
+static_assert(WF_RING >= WF_SLOTS && (WF_RING & (WF_RING - 1)) == 0 && WF_SLOTS < 2048, "ring / slot-id encoding");
 
 // Stages.  Loop stages (SDF, RMO, CLOUD) run bursts of a small loop body; the others are one-shot
-// bodies executed converged over up to 32 members.  A loop body never runs transition code: a
-// finished lane records its result and flips the stage, the transition happens later for a whole
-// group at once.
-enum : uint32_t { ST_DEAD = 0, ST_NEW, ST_SDF, ST_RMO, ST_CLOUD, ST_SDF_DONE, ST_RMO_DONE, ST_EVENT, ST_NEE_DONE, ST_COUNT };
+// bodies executed converged over up to 32 slots.  A loop body never runs transition code.
+enum : uint32_t { ST_NEW = 0, ST_SDF, ST_RMO, ST_CLOUD, ST_SDF_DONE, ST_RMO_DONE, ST_EVENT, ST_NEE_DONE, ST_COUNT };
 
 // pk word: stage[0:4) ratio[4] shadow[5] surface[6] vis[7] sc[8:13) lam[13:22) ev[22:24) rmo_ev[24:26) rmo_id[26:28) id[28:31)
 #define PK_STAGE(p) ((p)&15u)
@@ -61,15 +66,20 @@ DE_DEV uint32_t pk_set(uint32_t p, int shift, uint32_t mask, uint32_t v) { retur
 #define PK_SET_RMO_ID(p, v) pk_set(p, 26, 3u, v)
 #define PK_SET_ID(p, v) pk_set(p, 28, 7u, v)
 
-struct WarpPool {  // SoA: lane l touching slot s hits bank s%32
-    float ox[WF_N], oy[WF_N], oz[WF_N], dx[WF_N], dy[WF_N], dz[WF_N];
-    float thr[WF_N], L[WF_N];
-    uint32_t pix[WF_N], sample[WF_N], pk[WF_N], draw[WF_N];  // draw: rng draw index [0:24) | sdf iteration [24:32)
-    float t[WF_N], tmax[WF_N], aux[WF_N], isect[WF_N];       // aux: rmo_t (delta) or transmittance (ratio)
-    float mdx[WF_N], mdy[WF_N], mdz[WF_N];                    // main ray direction while the NEE ray is tracked
-    float nx[WF_N], ny[WF_N], nz[WF_N], m0[WF_N], m1[WF_N], m2[WF_N];  // surface normal, albedo, ocean, bathymetry
-    float na[WF_N], nb[WF_N];                                 // NEE factors: phase | brdf, n.l
-    uint8_t members[WF_N];
+struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
+    float ox[WF_SLOTS], oy[WF_SLOTS], oz[WF_SLOTS], dx[WF_SLOTS], dy[WF_SLOTS], dz[WF_SLOTS];
+    float thr[WF_SLOTS], L[WF_SLOTS];
+    uint32_t pix[WF_SLOTS], sample[WF_SLOTS], pk[WF_SLOTS], draw[WF_SLOTS];  // draw: rng slot index [0:24) | sdf iteration [24:32)
+    float t[WF_SLOTS], tmax[WF_SLOTS], aux[WF_SLOTS], isect[WF_SLOTS];       // aux: rmo_t (delta) or transmittance (ratio)
+    float mdx[WF_SLOTS], mdy[WF_SLOTS], mdz[WF_SLOTS];                        // main ray direction while the NEE ray is tracked
+    float nx[WF_SLOTS], ny[WF_SLOTS], nz[WF_SLOTS], m0[WF_SLOTS], m1[WF_SLOTS], m2[WF_SLOTS];  // surface normal, albedo, ocean, bathymetry
+    float na[WF_SLOTS], nb[WF_SLOTS];                                         // NEE factors: phase | brdf, n.l (nb doubles as the decision-slot word)
+    // per-stage MPMC ring queues of ready slots: entry = slot | (lap & 31) << 11
+    uint16_t ring[ST_COUNT][WF_RING];
+    unsigned int q_tail[ST_COUNT], q_head[ST_COUNT];
+    int q_avail[ST_COUNT];
+    int retired;     // slots that found no more work
+    int work_left;
 };
 
 struct WfParams {
@@ -135,6 +145,65 @@ struct Ctx {  // per-warp context
     Counters &cn;
     int lane;
 };
+
+// ---- stage queues -------------------------------------------------------------------------
+// push: reserve a ring position, write the lap-tagged entry, publish it.  pop: take up to `want`
+// published entries (semaphore style), then read the reserved positions, spinning on the lap tag
+// for the rare entry whose producer reserved earlier but has not written yet.
+DE_DEV void q_push(WarpPool &p, uint32_t st, int slot) {
+    unsigned int pos = atomicAdd(&p.q_tail[st], 1u);
+    volatile uint16_t *r = p.ring[st];
+    r[pos & (WF_RING - 1)] = (uint16_t)((unsigned)slot | (((pos / WF_RING) & 31u) << 11));
+    __threadfence_block();
+    atomicAdd(&p.q_avail[st], 1);
+}
+// warp-aggregated push of the lanes in `mask` (all to stage st): one reservation for the group
+DE_DEV void q_push_group(WarpPool &p, uint32_t st, int slot, unsigned mask, int lane) {
+    int n = __popc(mask), leader = __ffs(mask) - 1;
+    unsigned int base = 0u;
+    if (lane == leader) base = atomicAdd(&p.q_tail[st], (unsigned)n);
+    base = __shfl_sync(mask, base, leader);
+    unsigned int pos = base + (unsigned)__popc(mask & ((1u << lane) - 1u));
+    volatile uint16_t *r = p.ring[st];
+    r[pos & (WF_RING - 1)] = (uint16_t)((unsigned)slot | (((pos / WF_RING) & 31u) << 11));
+    __threadfence_block();
+    __syncwarp(mask);
+    if (lane == leader) atomicAdd(&p.q_avail[st], n);
+}
+// one-shot stages: every lane with a slot pushes it to stage PK_STAGE(npk); grouped per target stage
+DE_DEV void q_push_sorted(WarpPool &p, bool has, uint32_t st, int slot, int lane) {
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, has);
+    while (todo) {
+        int leader = __ffs(todo) - 1;
+        uint32_t lst = __shfl_sync(0xFFFFFFFFu, st, leader);
+        unsigned grp = __ballot_sync(0xFFFFFFFFu, has && st == lst);
+        if (has && st == lst) q_push_group(p, lst, slot, grp, lane);
+        todo &= ~grp;
+    }
+}
+// warp-collective: returns the number of slots obtained (<= want); lane i < n receives its slot
+DE_DEV int q_pop(WarpPool &p, uint32_t st, int want, int lane, int &slot) {
+    unsigned int base = 0u;
+    int n = 0;
+    if (lane == 0) {
+        int a = atomicSub(&p.q_avail[st], want);
+        n = a >= want ? want : (a > 0 ? a : 0);
+        if (n < want) atomicAdd(&p.q_avail[st], want - n);
+        if (n) base = atomicAdd(&p.q_head[st], (unsigned)n);
+    }
+    n = __shfl_sync(0xFFFFFFFFu, n, 0);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    slot = -1;
+    if (lane < n) {
+        unsigned int pos = base + (unsigned)lane;
+        const unsigned tag = (pos / WF_RING) & 31u;
+        volatile uint16_t *r = p.ring[st];
+        unsigned e;
+        do { e = r[pos & (WF_RING - 1)]; } while ((e >> 11) != tag);
+        slot = (int)(e & 2047u);
+    }
+    return n;
+}
 
 DE_DEV RngW load_rng(const Ctx &c, int slot, uint32_t pk) {
     RngW r;
@@ -217,9 +286,7 @@ DE_DEV uint32_t begin_segment(const Ctx &c, int slot, uint32_t pk, float3 o, flo
 
 // ST_SDF_DONE: what follows intersect_land -- main ray: sample_interaction; shadow ray: visibility +
 // sample_transmittance (pathtracer.py:422-430).  t[slot] holds the intersection distance.
-DE_DEV void stage_sdf_done(Ctx &c, int n_members) {
-    int slot = c.lane < n_members ? c.pool.members[c.lane] : -1;
-    if (slot < 0) return;
+DE_DEV uint32_t stage_sdf_done(Ctx &c, int slot) {
     uint32_t pk = c.pool.pk[slot];
     float3 o = ld_o(c, slot), d = ld_d(c, slot);
     float isect = c.pool.t[slot];
@@ -231,34 +298,33 @@ DE_DEV void stage_sdf_done(Ctx &c, int n_members) {
         pk &= ~PK_SHADOW;
     }
     c.pool.isect[slot] = isect;
-    c.pool.pk[slot] = setup_rmo(c, slot, pk, o, d, shadow);
+    return setup_rmo(c, slot, pk, o, d, shadow);
 }
 // ST_RMO_DONE: between the rmo pass and the cloud pass of either tracker
-DE_DEV void stage_rmo_done(Ctx &c, int n_members) {
-    int slot = c.lane < n_members ? c.pool.members[c.lane] : -1;
-    if (slot < 0) return;
+DE_DEV uint32_t stage_rmo_done(Ctx &c, int slot) {
     uint32_t pk = c.pool.pk[slot];
     float3 o = ld_o(c, slot), d = ld_d(c, slot);
-    c.pool.pk[slot] = (pk & PK_RATIO) ? setup_cloud_ratio(c, slot, pk, o, d) : setup_cloud_delta(c, slot, pk, o, d);
+    return (pk & PK_RATIO) ? setup_cloud_ratio(c, slot, pk, o, d) : setup_cloud_delta(c, slot, pk, o, d);
 }
 
 // ------------------------------------------------------------------ path start / end
-// ST_NEW: Renderer.render prologue for one sample (renderer.py:305-314); warp-collective work claim
-template <bool COUNT> DE_DEV bool stage_new(Ctx &c, int n_members) {
+// ST_NEW (free slots): Renderer.render prologue for one sample (renderer.py:305-314).  Called with
+// exactly 32 free slots, one per lane; claims one work chunk = 32 neighbouring pixels, one sample.
+// Returns the new pk (ST_SDF), ST_NEW to hand the slot back (pixel outside the window), or ~0u
+// when no work is left.
+template <bool COUNT> DE_DEV uint32_t stage_new(Ctx &c, int slot) {
     const unsigned full = 0xFFFFFFFFu;
     const WfParams &P = c.P;
     unsigned chunk = 0u;
     if (c.lane == 0) chunk = atomicAdd(P.next, 1u);
     chunk = __shfl_sync(full, chunk, 0);
-    if (chunk >= P.n_chunks) return false;  // no work left: caller retires the ST_NEW slots
-    int slot = c.lane < n_members ? c.pool.members[c.lane] : -1;
-    if (slot < 0) return true;  // unreachable: the caller passes exactly 32 members
+    if (chunk >= P.n_chunks) return ~0u;
     unsigned index = chunk * 32u + (unsigned)c.lane;
     unsigned in_tile = index & 127u, ts = index >> 7;
     unsigned sp = ts % (unsigned)P.n_spp, tile = ts / (unsigned)P.n_spp;
     int px = P.x0 + (int)(tile % (unsigned)P.tiles_x) * kDeTileW + (int)(in_tile & 15u);
     int py = P.y0 + (int)(tile / (unsigned)P.tiles_x) * kDeTileH + (int)(in_tile >> 4);
-    if (px >= P.x0 + P.w || py >= P.y0 + P.h) return true;  // outside the window: slot stays ST_NEW
+    if (px >= P.x0 + P.w || py >= P.y0 + P.h) return ST_NEW;
     RngW rng;
     rng.key0 = P.seed; rng.key1 = (uint32_t)(py * c.s.W + px); rng.sample = P.first_sample + sp; rng.bounce = 0u; rng.draw = 0u; rng.valid = false;
     int bin = spectrum_bin(c.s.cdf, rng.next());
@@ -267,13 +333,11 @@ template <bool COUNT> DE_DEV bool stage_new(Ctx &c, int n_members) {
     c.pool.pix[slot] = rng.key1; c.pool.sample[slot] = rng.sample;
     c.pool.thr[slot] = 1.0f; c.pool.L[slot] = 0.0f;
     st_o(c, slot, c.s.cam_pos); st_d(c, slot, dir);
-    uint32_t pk = PK_SET_LAM(0u, (uint32_t)bin);
-    c.pool.pk[slot] = begin_segment(c, slot, pk, c.s.cam_pos, dir);
     DE_COUNT(c.cn, C_SEGMENTS);
-    return true;
+    return begin_segment(c, slot, PK_SET_LAM(0u, (uint32_t)bin), c.s.cam_pos, dir);
 }
-// pathtracer.py:455-469 + renderer.py:329-330
-template <bool COUNT> DE_DEV void end_path(Ctx &c, int slot, uint32_t pk, bool primary_miss, float3 dir) {
+// pathtracer.py:455-469 + renderer.py:329-330; frees the slot
+template <bool COUNT> DE_DEV uint32_t end_path(Ctx &c, int slot, uint32_t pk, bool primary_miss, float3 dir) {
     const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
     float Lr = c.pool.L[slot];
     if (primary_miss) {
@@ -290,22 +354,47 @@ template <bool COUNT> DE_DEV void end_path(Ctx &c, int slot, uint32_t pk, bool p
         float *a = c.P.accum + (size_t)c.pool.pix[slot] * 3;
         atomicAdd(a, rgb.x); atomicAdd(a + 1, rgb.y); atomicAdd(a + 2, rgb.z);
     }
-    c.pool.pk[slot] = ST_NEW;
+    return ST_NEW;
 }
 
 // ------------------------------------------------------------------ loop stages
-// SDF sphere tracing, one iteration per loop trip (pathtracer.py:37-44)
-template <bool COUNT> DE_DEV void burst_sdf(Ctx &c, int n_members) {
+// Burst bookkeeping at the converged point of a loop trip.  Finished lanes keep (slot, next stage)
+// in registers; only when enough lanes idle (or none is busy) are they pushed -- grouped per target
+// queue, one reservation per group -- and the idle lanes refilled from this stage's own queue.
+// Returns the active mask after the refill; lanes that received a slot have take_new = true.
+DE_DEV unsigned burst_sync(Ctx &c, uint32_t st, bool active, bool &pending, uint32_t pend_st, int pend_slot, int &slot, bool &take_new) {
     const unsigned full = 0xFFFFFFFFu;
-    int next = min(n_members, 32);
-    const int min_active = min(WF_MIN_ACTIVE, (next + 1) / 2);
-    int slot = c.lane < n_members ? c.pool.members[c.lane] : -1;
+    take_new = false;
+    unsigned am = __ballot_sync(full, active);
+    int idle = 32 - __popc(am);
+    if (idle < WF_REFILL_MIN && am != 0u) return am;
+    q_push_sorted(c.pool, pending, pend_st, pend_slot, c.lane);
+    pending = false;
+    int av = 0;
+    if (c.lane == 0) av = *(volatile int *)&c.pool.q_avail[st];
+    if (__shfl_sync(full, av, 0) <= 0) return am;  // warp-uniform decision
+    int got_slot;
+    int n = q_pop(c.pool, st, idle, c.lane, got_slot);
+    if (n == 0) return am;
+    int rank = __popc(~am & ((1u << c.lane) - 1u));
+    int mine = __shfl_sync(full, got_slot, rank & 31);
+    if (!active && rank < n) { slot = mine; take_new = true; }
+    return am | __ballot_sync(full, take_new);
+}
+
+// SDF sphere tracing, one iteration per loop trip (pathtracer.py:37-44)
+template <bool COUNT> DE_DEV void burst_sdf(Ctx &c, int slot) {
+    const unsigned full = 0xFFFFFFFFu;
     bool active = slot >= 0;
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
     float t = 0.0f;
     uint32_t iter = 0u;
-    if (active) { o = ld_o(c, slot); d = ld_d(c, slot); t = c.pool.t[slot]; iter = c.pool.draw[slot] >> 24; }
+    auto load = [&]() { o = ld_o(c, slot); d = ld_d(c, slot); t = c.pool.t[slot]; iter = c.pool.draw[slot] >> 24; };
+    if (active) load();
+    const int min_active = min(WF_MIN_ACTIVE, (__popc(__ballot_sync(full, active)) + 1) / 2);
     const float scale = c.s.land_height_scale;
+    bool pending = false;
+    int pend_slot = -1;
     for (int it = 0; it < WF_BURST; ++it) {
         if (active) {
             float3 ro = o + d * t;
@@ -316,24 +405,20 @@ template <bool COUNT> DE_DEV void burst_sdf(Ctx &c, int n_members) {
             if (t > 63710000.0f || fabsf(dist) < t * 0.0001f || iter >= 250u) {
                 c.pool.t[slot] = t < 63710000.0f ? t : -1.0f;
                 c.pool.pk[slot] = PK_SET_STAGE(c.pool.pk[slot], ST_SDF_DONE);
-                active = false;
+                active = false; pending = true; pend_slot = slot;
             }
         }
-        unsigned am = __ballot_sync(full, active);
-        if (next < n_members) {
-            unsigned need = ~am;
-            int rank = __popc(need & ((1u << c.lane) - 1u));
-            if (!active && next + rank < n_members) {
-                slot = c.pool.members[next + rank];
-                o = ld_o(c, slot); d = ld_d(c, slot); t = c.pool.t[slot]; iter = c.pool.draw[slot] >> 24;
-                active = true;
-            }
-            next = min(n_members, next + __popc(need));
-            am = __ballot_sync(full, active);
-        }
+        bool take;
+        unsigned am = burst_sync(c, ST_SDF, active, pending, ST_SDF_DONE, pend_slot, slot, take);
+        if (take) { load(); active = true; }
         if (__popc(am) < min_active) break;
     }
-    if (active) { c.pool.t[slot] = t; c.pool.draw[slot] = (c.pool.draw[slot] & 0xFFFFFFu) | (iter << 24); }
+    q_push_sorted(c.pool, pending, ST_SDF_DONE, pend_slot, c.lane);
+    unsigned am = __ballot_sync(full, active);
+    if (active) {
+        c.pool.t[slot] = t; c.pool.draw[slot] = (c.pool.draw[slot] & 0xFFFFFFu) | (iter << 24);
+        q_push_group(c.pool, ST_SDF, slot, am, c.lane);
+    }
 }
 
 // delta / ratio tracking through Rayleigh+Mie+ozone (IS_CLOUD=false) or the cloud shell (true)
@@ -341,13 +426,11 @@ template <bool COUNT> DE_DEV void burst_sdf(Ctx &c, int n_members) {
 // (words 0,1 and 2,3: free flight + acceptance test; a ratio step leaves its second word unused),
 // so the RNG is issued converged with static word selection.  A real collision only records the
 // slot of its scatter/absorb draw (pathtracer.py:270); ST_EVENT evaluates it for the winner.
-template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int n_members) {
+template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int slot) {
     const unsigned full = 0xFFFFFFFFu;
-    int next = min(n_members, 32);
-    const int min_active = min(WF_MIN_ACTIVE, (next + 1) / 2);
-    int slot = c.lane < n_members ? c.pool.members[c.lane] : -1;
+    const uint32_t ST_SELF = IS_CLOUD ? ST_CLOUD : ST_RMO;
     bool active = slot >= 0;
-    float3 d = f3(0, 0, 1), pos = f3(0, 0, 0), ext = f3(0, 0, 0);
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), ext = f3(0, 0, 0);
     float t = 0.0f, tmax = 0.0f, T = 1.0f, max_ext = 1.0f, ext_cloud = 0.0f;
     uint32_t pk = 0u, blk = 0u, key1 = 0u, smp = 0u;
     auto load = [&]() {
@@ -356,11 +439,15 @@ template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int n_membe
         pk = c.pool.pk[slot];
         key1 = c.pool.pix[slot]; smp = c.pool.sample[slot];
         blk = ((c.pool.draw[slot] & 0xFFFFFFu) + 3u) >> 2;  // passes start on a block boundary; trips end on one
-        pos = ld_o(c, slot) + d * t;
+        o = ld_o(c, slot);
         if (IS_CLOUD) { ext_cloud = cloud_ext_of(PK_SC(pk)); max_ext = ext_cloud * kCloudsDensity; }
         else { const LambdaRow &lr = c.s.lam[PK_LAM(pk)]; ext = f3(lr.ext_r, lr.ext_m, lr.ext_o); max_ext = lr.max_ext_rmo; }
     };
     if (active) load();
+    const int min_active = min(WF_MIN_ACTIVE, (__popc(__ballot_sync(full, active)) + 1) / 2);
+    bool pending = false;
+    int pend_slot = -1;
+    uint32_t pend_st = ST_RMO_DONE;
     for (int it = 0; it < WF_BURST / 2; ++it) {
         if (active) {
             const bool ratio = (pk & PK_RATIO) != 0u;
@@ -369,9 +456,8 @@ template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int n_membe
             uint32_t ev = 0u, id = IS_CLOUD ? 3u : 0u, draw_after = 0u;
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
-                float t_step = -logf(u32_to_unit(h ? rb.z : rb.x)) / max_ext;
-                pos = pos + d * t_step;
-                t += t_step;
+                t += -logf(u32_to_unit(h ? rb.z : rb.x)) / max_ext;
+                const float3 pos = o + d * t;  // from the origin every time: independent of where bursts were cut
                 if (t >= tmax) { done = true; draw_after = 4u * blk + 2u * h + 1u; break; }
                 float es0 = 0.0f, es1 = 0.0f, es2 = 0.0f, sum;
                 if (IS_CLOUD) {
@@ -423,26 +509,25 @@ template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int n_membe
                     npk = PK_SET_STAGE(npk, ST_RMO_DONE);
                 }
                 c.pool.pk[slot] = npk;
-                active = false;
+                pend_st = PK_STAGE(npk);  // RMO_DONE, or EVENT (delta) / NEE_DONE (ratio) after the cloud pass
+                active = false; pending = true; pend_slot = slot;
             }
         }
-        unsigned am = __ballot_sync(full, active);
-        if (next < n_members) {
-            unsigned need = ~am;
-            int rank = __popc(need & ((1u << c.lane) - 1u));
-            if (!active && next + rank < n_members) { slot = c.pool.members[next + rank]; load(); active = true; }
-            next = min(n_members, next + __popc(need));
-            am = __ballot_sync(full, active);
-        }
+        bool take;
+        unsigned am = burst_sync(c, ST_SELF, active, pending, pend_st, pend_slot, slot, take);
+        if (take) { load(); active = true; }
         if (__popc(am) < min_active) break;
     }
-    if (active) { c.pool.t[slot] = t; if (pk & PK_RATIO) c.pool.aux[slot] = T; store_draw(c, slot, 4u * blk, 0u); }
+    q_push_sorted(c.pool, pending, pend_st, pend_slot, c.lane);
+    unsigned am = __ballot_sync(full, active);
+    if (active) {
+        c.pool.t[slot] = t; if (pk & PK_RATIO) c.pool.aux[slot] = T; store_draw(c, slot, 4u * blk, 0u);
+        q_push_group(c.pool, ST_SELF, slot, am, c.lane);
+    }
 }
 
 // ST_EVENT: after sample_interaction, pathtracer.py:369-444 up to the point where the NEE ray is traced
-template <bool COUNT> DE_DEV void stage_event(Ctx &c, int n_members) {
-    int slot = c.lane < n_members ? c.pool.members[c.lane] : -1;
-    if (slot < 0) return;
+template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
     uint32_t pk = c.pool.pk[slot];
     const uint32_t sc = PK_SC(pk);
     const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
@@ -459,7 +544,7 @@ template <bool COUNT> DE_DEV void stage_event(Ctx &c, int n_members) {
     if (sc > 9u && id == (uint32_t)kCloud) id = kIsoCloud;
     rng.align();
     float3 light_dir = sample_cone_oriented(c.dv.sun_cos_angle, c.dv.light_dir, rng);
-    if (ev == (uint32_t)kAbsorbEvent) { end_path<COUNT>(c, slot, pk, false, d); return; }
+    if (ev == (uint32_t)kAbsorbEvent) return end_path<COUNT>(c, slot, pk, false, d);
     if (ev == (uint32_t)kScatterEvent) {
         float3 ipos = o + d * c.pool.t[slot];
         bool blocked = rsi(ipos, light_dir, kPlanetR).y > 0.0f;
@@ -468,9 +553,9 @@ template <bool COUNT> DE_DEV void stage_event(Ctx &c, int n_members) {
         st_o(c, slot, ipos); st_d(c, slot, light_dir);
         pk = PK_SET_ID(pk, id) & ~PK_SURFACE;
         store_draw(c, slot, rng.draw, 0u);
-        if (blocked) { c.pool.aux[slot] = 0.0f; c.pool.pk[slot] = PK_SET_STAGE(pk, ST_NEE_DONE); }
-        else { c.pool.isect[slot] = -1.0f; c.pool.pk[slot] = setup_rmo(c, slot, pk, ipos, light_dir, true); }
-        return;
+        if (blocked) { c.pool.aux[slot] = 0.0f; return PK_SET_STAGE(pk, ST_NEE_DONE); }
+        c.pool.isect[slot] = -1.0f;
+        return setup_rmo(c, slot, pk, ipos, light_dir, true);
     }
     float earth_isect = c.pool.isect[slot];
     if (earth_isect > 0.0f) {
@@ -499,16 +584,13 @@ template <bool COUNT> DE_DEV void stage_event(Ctx &c, int n_members) {
         c.pool.mdx[slot] = d.x; c.pool.mdy[slot] = d.y; c.pool.mdz[slot] = d.z;
         st_o(c, slot, offset_pos); st_d(c, slot, light_dir);
         pk |= PK_SURFACE | PK_SHADOW;
-        c.pool.pk[slot] = setup_sdf(c, slot, pk, offset_pos, light_dir, rng.draw);
-        return;
+        return setup_sdf(c, slot, pk, offset_pos, light_dir, rng.draw);
     }
-    end_path<COUNT>(c, slot, pk, sc == 0u, d);  // escaped (pathtracer.py:441-444)
+    return end_path<COUNT>(c, slot, pk, sc == 0u, d);  // escaped (pathtracer.py:441-444)
 }
 
 // ST_NEE_DONE: after the NEE transmittance, pathtracer.py:394-401 / 431-439, Russian roulette :447-453, next segment
-template <bool COUNT> DE_DEV void stage_nee_done(Ctx &c, int n_members) {
-    int slot = c.lane < n_members ? c.pool.members[c.lane] : -1;
-    if (slot < 0) return;
+template <bool COUNT> DE_DEV uint32_t stage_nee_done(Ctx &c, int slot) {
     uint32_t pk = c.pool.pk[slot];
     uint32_t sc = PK_SC(pk);
     const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
@@ -541,77 +623,85 @@ template <bool COUNT> DE_DEV void stage_nee_done(Ctx &c, int n_members) {
         else thr /= 1.0f - p;
     }
     ++sc;
-    if (terminate || sc >= 25u) { end_path<COUNT>(c, slot, pk, false, nd); return; }
+    if (terminate || sc >= 25u) return end_path<COUNT>(c, slot, pk, false, nd);
     c.pool.thr[slot] = thr;
     st_d(c, slot, nd);
     pk = PK_SET_SC(pk, sc);
     DE_COUNT(c.cn, C_SEGMENTS);
-    c.pool.pk[slot] = begin_segment(c, slot, pk, o, nd);
+    return begin_segment(c, slot, pk, o, nd);
 }
 
 // ------------------------------------------------------------------ the persistent kernel
 template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_render_wavefront(const __grid_constant__ DevScene s, const __grid_constant__ WfParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpPool *pools = reinterpret_cast<WarpPool *>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpPool &pool = *reinterpret_cast<WarpPool *>(smem_raw);
+    const int lane = threadIdx.x & 31;
     const unsigned full = 0xFFFFFFFFu;
     const DevDerived dv = *s.derived;
     Counters cn;
     cn.clear();
-    Ctx c{s, dv, P, pools[warp], cn, lane};
-    WarpPool &pool = c.pool;
-    for (int k = lane; k < WF_N; k += 32) pool.pk[k] = ST_NEW;
-    __syncwarp();
-    bool work_left = true;
+    Ctx c{s, dv, P, pool, cn, lane};
+    const int pref = (threadIdx.x >> 5) % 4 == 0 ? (int)ST_SDF : ((threadIdx.x >> 5) % 4 == 1 ? (int)ST_RMO : (int)ST_CLOUD);
+    // all slots start free (queue ST_NEW); ring entries carry lap tag 31 until first written
+    for (int k = threadIdx.x; k < ST_COUNT * WF_RING; k += blockDim.x) (&pool.ring[0][0])[k] = 0xFFFFu;
+    __syncthreads();
+    for (int k = threadIdx.x; k < WF_SLOTS; k += blockDim.x) pool.ring[ST_NEW][k] = (uint16_t)k;
+    if (threadIdx.x < ST_COUNT) {
+        pool.q_tail[threadIdx.x] = threadIdx.x == ST_NEW ? WF_SLOTS : 0u;
+        pool.q_head[threadIdx.x] = 0u;
+        pool.q_avail[threadIdx.x] = threadIdx.x == ST_NEW ? WF_SLOTS : 0;
+    }
+    if (threadIdx.x == 0) { pool.retired = 0; pool.work_left = 1; }
+    __syncthreads();
     for (;;) {
-        // 1. census of stages (warp ballots over the pool's stage words)
-        int cnt[ST_COUNT];
+        // 1. pick the fullest stage queue (free slots only count in whole chunks of 32 while work remains)
+        int wl = 0;
+        if (lane == 0) wl = *(volatile int *)&pool.work_left | (*(volatile int *)&pool.retired >= WF_SLOTS ? 2 : 0);
+        wl = __shfl_sync(full, wl, 0);  // warp-uniform snapshot
+        const bool work_left = (wl & 1) != 0;
+        int av = lane < (int)ST_COUNT ? *(volatile int *)&pool.q_avail[lane] : 0;
+        if (lane == (int)ST_NEW && work_left && av < 32) av = 0;
+        // warps of one SM sub-partition (warp % 4) prefer the same loop stage, so its instruction-cache
+        // slice holds one loop body; any other queue wins only when it is clearly fuller
+        if (lane == pref && av >= 32) av += WF_SLOTS;
+        int key = av > 0 ? (av << 4) | lane : 0;
 #pragma unroll
-        for (int q = 0; q < ST_COUNT; ++q) cnt[q] = 0;
-        for (int k = 0; k < WF_N; k += 32) {
-            uint32_t st = PK_STAGE(pool.pk[k + lane]);
-#pragma unroll
-            for (int q = 1; q < ST_COUNT; ++q) cnt[q] += __popc(__ballot_sync(full, st == (uint32_t)q));
+        for (int o = 4; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(full, key, o));
+        key = __shfl_sync(full, key, 0);
+        if (key == 0) {
+            if (wl & 2) break;  // every slot found the work counter exhausted
+            __nanosleep(64);
+            continue;
         }
-        if (!work_left) cnt[ST_NEW] = 0;
-        // regeneration needs a whole chunk of 32 free slots while work is plentiful; the other
-        // stages compete on population
-        int best = 0, best_n = 0;
-#pragma unroll
-        for (int q = 1; q < ST_COUNT; ++q) {
-            int n = cnt[q];
-            if (q == ST_NEW && n < 32) n = 0;
-            if (n > best_n) { best_n = n; best = q; }
-        }
-        if (best_n == 0) break;  // pool drained (free slots always come in groups >= 32 until then: WF_N >= 64)
-        // 2. compact the members of that stage (warp-ballot compaction)
-        int base = 0;
-        for (int k = 0; k < WF_N; k += 32) {
-            bool is = PK_STAGE(pool.pk[k + lane]) == (uint32_t)best;
-            unsigned m = __ballot_sync(full, is);
-            if (is) pool.members[base + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(k + lane);
-            base += __popc(m);
-        }
-        __syncwarp();
-        // 3. run it
-        if (best == ST_SDF) burst_sdf<COUNT>(c, best_n);
-        else if (best == ST_RMO) burst_track<COUNT, false>(c, best_n);
-        else if (best == ST_CLOUD) burst_track<COUNT, true>(c, best_n);
+        const uint32_t st = (uint32_t)(key & 15);
+        // 2. take up to 32 ready slots
+        int slot;
+        int n = q_pop(pool, st, 32, lane, slot);
+        if (n == 0) continue;
+        // 3. run the stage
+        if (st == ST_SDF) burst_sdf<COUNT>(c, slot);
+        else if (st == ST_RMO) burst_track<COUNT, false>(c, slot);
+        else if (st == ST_CLOUD) burst_track<COUNT, true>(c, slot);
         else {
-            // a work chunk is exactly 32 paths: regeneration only runs on whole groups of 32 free slots
-            const int lim = best == ST_NEW ? (best_n & ~31) : best_n;
-            for (int b = 0; b < lim; b += 32) {
-                if (b) { uint8_t mv = lane + b < best_n ? pool.members[lane + b] : 0; __syncwarp(); pool.members[lane] = mv; __syncwarp(); }
-                int n = min(32, best_n - b);
-                if (best == ST_SDF_DONE) stage_sdf_done(c, n);
-                else if (best == ST_RMO_DONE) stage_rmo_done(c, n);
-                else if (best == ST_EVENT) stage_event<COUNT>(c, n);
-                else if (best == ST_NEE_DONE) stage_nee_done<COUNT>(c, n);
-                else { if (!stage_new<COUNT>(c, n)) { work_left = false; break; } }
-                __syncwarp();
+            uint32_t npk = 0u;
+            bool has = slot >= 0;
+            if (st == ST_NEW) {
+                if (!work_left) { if (lane == 0) atomicAdd(&pool.retired, n); continue; }
+                if (n < 32) { q_push_sorted(pool, has, ST_NEW, slot, lane); continue; }  // lost a race for a whole chunk
+                npk = stage_new<COUNT>(c, slot);
+                if (npk == ~0u) {  // work counter exhausted
+                    if (lane == 0) { pool.work_left = 0; atomicAdd(&pool.retired, 32); }
+                    continue;
+                }
+            } else if (has) {
+                if (st == ST_SDF_DONE) npk = stage_sdf_done(c, slot);
+                else if (st == ST_RMO_DONE) npk = stage_rmo_done(c, slot);
+                else if (st == ST_EVENT) npk = stage_event<COUNT>(c, slot);
+                else npk = stage_nee_done<COUNT>(c, slot);
             }
+            if (has) c.pool.pk[slot] = npk;
+            q_push_sorted(pool, has, PK_STAGE(npk), slot, lane);
         }
-        __syncwarp();
     }
     if (COUNT) cn.flush(s.counters);
 }
@@ -639,7 +729,7 @@ void de_wavefront_free(DeWavefrontState *st) {
 void de_wavefront_render(DeWavefrontState *st, const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0,
                          int w, int h, bool count, cudaStream_t stream) {
     using namespace de_fast;
-    size_t smem = sizeof(WarpPool) * WF_WARPS;
+    size_t smem = sizeof(WarpPool);
     if (!st->attr_set) {
         cudaFuncSetAttribute(k_render_wavefront<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_render_wavefront<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
