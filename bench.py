@@ -163,9 +163,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W, H = map(int, a.res.split("x"))
     tw, th = map(int, a.tex.split("x"))
-    assert a.spp % world == 0, "spp must divide by the number of GPUs"
-    spp_local = a.spp // world
-    first = rank * spp_local
+    from digital_earth_b200.distributed import sample_slice, reduce_accumulation
+    first, spp_local = sample_slice(a.spp, rank, world)
 
     tex = textures_for(a, tw, th)
     cfg = scene_cfg(a)
@@ -181,8 +180,7 @@ def main():
             r.apply_config(cfg)   # host -> device: scene parameters for this frame
         r.reset_framebuffer()
         r.accumulate(spp_local, first_sample=first)
-        if world > 1:
-            dist.reduce(r.color_buffer, dst=0, op=dist.ReduceOp.SUM)  # NCCL over NVLink: the path's one exchange step
+        reduce_accumulation(r.color_buffer, dst=0)  # ncclReduce(sum) over NVLink: the path's one exchange step (no-op at N=1)
         if e2e and rank == 0:
             img = r.fetch_image(spp=a.spp)
             host_img.copy_(img.permute(1, 0, 2), non_blocking=True)  # device -> pinned host ([H][W][3] storage order)
