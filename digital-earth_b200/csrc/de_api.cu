@@ -26,6 +26,7 @@ struct de_ctx {
     LambdaRow *d_lam = nullptr;
     DevDerived *d_derived = nullptr;
     float *d_accum = nullptr, *d_image = nullptr;
+    uint8_t *d_cloud_max = nullptr;
     unsigned long long *d_counters = nullptr;
     DeWavefrontState *wf = nullptr;
     std::string err;
@@ -125,6 +126,7 @@ void de_destroy(de_ctx *ctx) {
     }
     de_wavefront_free(ctx->wf);
     cudaFree(ctx->d_cie); cudaFree(ctx->d_s2s); cudaFree(ctx->d_o3); cudaFree(ctx->d_crf); cudaFree(ctx->d_cdf);
+    cudaFree(ctx->d_cloud_max);
     cudaFree(ctx->d_lam); cudaFree(ctx->d_derived); cudaFree(ctx->d_accum); cudaFree(ctx->d_image); cudaFree(ctx->d_counters);
     delete ctx;
 }
@@ -193,6 +195,15 @@ int de_upload_texture(de_ctx *ctx, int slot, const uint8_t *host, int w, int h, 
     CU(cudaCreateTextureObject(&t.obj, &rd, &td, nullptr));
     t.data = ctx->d_tex[slot]; t.w = w; t.h = h; t.c = channels;
     ctx->have_tex[slot] = true;
+    if (slot == DE_TEX_CLOUDS) {  // coarse max-map for the local tracking majorant (product flavour)
+        int b = w / 256 > 8 ? w / 256 : 8, cw = (w + b - 1) / b, ch = (h + b - 1) / b;
+        cudaFree(ctx->d_cloud_max); ctx->d_cloud_max = nullptr;
+        CU(cudaMalloc(&ctx->d_cloud_max, (size_t)cw * ch));
+        de_fast::launch_build_cloud_max(ctx->d_tex[slot], w, h, b, ctx->d_cloud_max, cw, ch, ctx->stream);
+        int rc_ = check_launch(ctx, "build_cloud_max");
+        if (rc_) return rc_;
+        ctx->scene.cloud_max = ctx->d_cloud_max; ctx->scene.cm_w = cw; ctx->scene.cm_h = ch; ctx->scene.cm_b = b;
+    }
     if (slot == DE_TEX_TOPOGRAPHY) ctx->derived_dirty = true;
     CU(cudaStreamSynchronize(ctx->stream));  // host buffer may be released by the caller
     return DE_OK;

@@ -255,6 +255,33 @@ DE_DEV float2 sphere_uv(float3 pos) {
 }
 DE_DEV float sample_sphere_r8(const DevTex &t, float3 pos) { float2 uv = sphere_uv(pos); return tex_r8(t, uv.x, uv.y); }
 DE_DEV float3 sample_sphere_rgb8(const DevTex &t, float3 pos) { float2 uv = sphere_uv(pos); return tex_rgb8(t, uv.x, uv.y); }
+#if !DE_EXACT
+// Upper bound of the cloud texture along the part [ts, tm] of a ray (product flavour).
+// A straight ray projects onto a great-circle arc: longitude is monotone along it (arcs shorter than
+// pi that stay away from the poles), latitude leaves the endpoint range by at most theta/2.  The
+// bound is the maximum of the dilated coarse map over that lat-long box; 1.0 (no information)
+// whenever the box is unsafe (date-line crossing, polar caps, long arcs, too many cells).
+DE_DEV float cloud_segment_cmax(const DevScene &s, float3 o, float3 d, float ts, float tm) {
+    if (!s.cloud_max) return 1.0f;
+    float theta = (tm - ts) * (1.0f / 6375000.0f);
+    if (!(theta < 0.25f)) return 1.0f;
+    float2 a = sphere_uv(o + d * ts), b = sphere_uv(o + d * tm);
+    if (fabsf(a.x - b.x) > 0.4f) return 1.0f;
+    float pad = theta * (0.5f / kPi) + 1e-4f;
+    float vlo = fminf(a.y, b.y) - pad, vhi = fmaxf(a.y, b.y) + pad;
+    if (vlo < 0.05f || vhi > 0.95f) return 1.0f;
+    float sx = (float)s.tex[3].w / (float)s.cm_b, sy = (float)s.tex[3].h / (float)s.cm_b;
+    int cu0 = max((int)((fminf(a.x, b.x) - 1e-4f) * sx), 0), cu1 = min((int)((fmaxf(a.x, b.x) + 1e-4f) * sx), s.cm_w - 1);
+    int cv0 = max((int)(vlo * sy), 0), cv1 = min((int)(vhi * sy), s.cm_h - 1);
+    if ((cu1 - cu0 + 1) * (cv1 - cv0 + 1) > 48) return 1.0f;
+    unsigned m = 0u;
+    for (int cv = cv0; cv <= cv1; ++cv)
+        for (int cu = cu0; cu <= cu1; ++cu) m = max(m, (unsigned)__ldg(s.cloud_max + cv * s.cm_w + cu));
+    return (float)m * (1.0f / 255.0f);
+}
+// density majorant of get_clouds_density given a bound on the texture value (pathtracer.py:63-65)
+DE_DEV float cloud_density_bound(float cmax) { return cmax > 0.0f ? fmaxf(cmax, 0.4f) * kCloudsDensity : 0.0f; }
+#endif
 // generic float LUT texture [h][w][nc] (CIE 441x2x3, CRF 1024xNx3)
 DE_DEV float tex_f32(const float *d, int w, int h, int nc, int c, float u, float v) {
     Bilin b = bilin_setup(w, h, u, v);
@@ -273,6 +300,21 @@ DE_DEV float2 rsi(float3 pos, float3 dir, float r) {
     return make_float2(-b + -discr, -b + discr);
 }
 
+#if !DE_EXACT
+// Exact miss test for intersect_land (pathtracer.py:27-46), product flavour.  From the marching start
+// point p (distance s0 already travelled) the terrain SDF is >= alt - scale (heightmap <= 1).  The loop
+// only stops early when |dist| < 1e-4 * ray_dist.  If the lowest altitude the ray can still reach
+// (perigee if it is approaching, the start point if it is receding) clears the tallest terrain by more
+// than 1e-4 * (distance travelled until then) -- afterwards altitude grows like x^2/2r, which beats
+// 1e-4 x by construction -- every iterate keeps dist > threshold, ray_dist runs past 10 R and the
+// reference returns -1.  100 m of slack covers f32 cancellation for cameras at 5.7e7 m.
+DE_DEV bool land_surely_missed(float3 p, float3 dir, float s0, float scale) {
+    float b = dot(p, dir), r2 = dot(p, p);
+    float rmin2 = b >= 0.0f ? r2 : r2 - b * b;
+    float need = kPlanetR + scale + 1e-4f * (s0 + fmaxf(-b, 0.0f)) + 100.0f;
+    return rmin2 > need * need;
+}
+#endif
 // ---------------------------------------------------------------- medium densities (volume_rendering_models.py:229-277)
 DE_DEV float get_ozone_density(float h) {
     float h_km = h * 0.001f;

@@ -25,6 +25,9 @@ template <bool COUNT> DE_DEV float intersect_land(const DevScene &s, float3 pos,
     const float max_ray_dist = 63710000.0f;
     float2 rd = rsi(pos, dir, kAtmosUpper);
     if (rd.x > 0.0f) ray_dist = rd.x;
+#if !DE_EXACT
+    if (land_surely_missed(pos + dir * ray_dist, dir, ray_dist, height_scale)) return -1.0f;
+#endif
     for (int i = 0; i < 250; ++i) {
         float3 ro = pos + dir * ray_dist;
         float dist = land_sdf<COUNT>(s, ro, height_scale, cn);
@@ -149,6 +152,12 @@ DE_DEV int sample_interaction(const DevScene &s, float3 pos, float3 dir, float l
     float t = rmo_t;
     if (rmo_event == kNullEvent || rmo_t > t_start) {
         float cloud_t; int cloud_id;
+#if !DE_EXACT
+        if (t_start < t_max) {  // product flavour: local majorant from the coarse cloud max-map (unbiased: any bound works)
+            float bound = cloud_density_bound(cloud_segment_cmax(s, pos, dir, t_start, t_max));
+            if (bound == 0.0f) t_max = t_start; else max_cloud = ext_cloud * bound;
+        }
+#endif
         int cloud_event = delta_tracking<COUNT, true>(s, pos, dir, t_start, t_max, ext_rmo, ext_cloud, max_cloud, rng, cn, cloud_t, cloud_id);
         if (cloud_event > 0 && (cloud_t < rmo_t || rmo_event == kNullEvent)) { t = cloud_t; id = kCloud; event = cloud_event; }
     }
@@ -164,6 +173,12 @@ DE_DEV float sample_transmittance(const DevScene &s, float3 pos, float3 dir, flo
     if (atm.y < 0.0f) t_max = -1.0f;
     float T = ratio_tracking<COUNT, false>(s, pos, dir, t_start, t_max, ext_rmo, ext_cloud, max_rmo, rng, cn);
     intersect_cloud_limits(pos, dir, land_isection, t_start, t_max);
+#if !DE_EXACT
+    if (t_start < t_max) {
+        float bound = cloud_density_bound(cloud_segment_cmax(s, pos, dir, t_start, t_max));
+        if (bound == 0.0f) t_max = t_start; else max_cloud = ext_cloud * bound;
+    }
+#endif
     T *= ratio_tracking<COUNT, true>(s, pos, dir, t_start, t_max, ext_rmo, ext_cloud, max_cloud, rng, cn);
     return T;
 }

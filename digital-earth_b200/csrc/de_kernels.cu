@@ -52,6 +52,23 @@ void launch_resolve(const DevScene &s, const float *accum, float *out, int spp, 
     k_resolve<<<(n + 255) / 256, 256, 0, st>>>(s, accum, out, spp);
 }
 
+#if !DE_EXACT
+// coarse max-map of the cloud texture: cell (cx,cy) = max over its cm_b x cm_b texels dilated by one
+__global__ void k_build_cloud_max(const uint8_t *tex, int w, int h, int b, uint8_t *out, int cw, int ch) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cw * ch) return;
+    int cx = c % cw, cy = c / cw;
+    int x0 = max(cx * b - 1, 0), x1 = min(cx * b + b, w - 1), y0 = max(cy * b - 1, 0), y1 = min(cy * b + b, h - 1);
+    unsigned m = 0u;
+    for (int y = y0; y <= y1; ++y)
+        for (int x = x0; x <= x1; ++x) m = max(m, (unsigned)tex[(size_t)y * w + x]);
+    out[c] = (uint8_t)m;
+}
+void launch_build_cloud_max(const uint8_t *tex, int w, int h, int b, uint8_t *out, int cw, int ch, cudaStream_t st) {
+    k_build_cloud_max<<<(cw * ch + 127) / 128, 128, 0, st>>>(tex, w, h, b, out, cw, ch);
+}
+#endif
+
 #if DE_EXACT
 // ------------------------------------------------------------------ set-up kernels
 // SceneParameters + camera basis (renderer.py:230,272-277,293-302; pathtracer.py:20)

@@ -11,6 +11,7 @@ struct DeWavefrontState;  // de_wavefront.cuh
 
 namespace de_fast {
 DE_DECLARE_COMMON
+void launch_build_cloud_max(const uint8_t *tex, int w, int h, int b, uint8_t *out, int cw, int ch, cudaStream_t st);
 }
 namespace de_exact {
 DE_DECLARE_COMMON

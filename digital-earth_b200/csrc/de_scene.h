@@ -47,6 +47,10 @@ struct DevScene {
     int tonemapper, topo_tex_w;
     int W, H;
     unsigned long long *counters;  // DeCounters layout, or nullptr
+    // coarse max-map of the cloud texture (product flavour: local tracking majorant); cell = cm_b x cm_b
+    // texels, dilated by one texel for the bilinear footprint; nullptr disables it
+    const uint8_t *cloud_max;
+    int cm_w, cm_h, cm_b;
 };
 
 

@@ -24,7 +24,7 @@
 namespace de_fast {
 
 #ifndef WF_SLOTS
-#define WF_SLOTS 1792  // path states per CTA (one CTA per SM): 189 KB of state + 32 KB of queues
+#define WF_SLOTS 1728  // path states per CTA (one CTA per SM): 189 KB of state (28 words each) + 32 KB of queues
 #endif
 #ifndef WF_WARPS
 #define WF_WARPS 32
@@ -74,6 +74,7 @@ struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
     float mdx[WF_SLOTS], mdy[WF_SLOTS], mdz[WF_SLOTS];                        // main ray direction while the NEE ray is tracked
     float nx[WF_SLOTS], ny[WF_SLOTS], nz[WF_SLOTS], m0[WF_SLOTS], m1[WF_SLOTS], m2[WF_SLOTS];  // surface normal, albedo, ocean, bathymetry
     float na[WF_SLOTS], nb[WF_SLOTS];                                         // NEE factors: phase | brdf, n.l (nb doubles as the decision-slot word)
+    float cmj[WF_SLOTS];                                                      // cloud pass: local density majorant (0.029 * max(cmax, 0.4))
     // per-stage MPMC ring queues of ready slots: entry = slot | (lap & 31) << 11
     uint16_t ring[ST_COUNT][WF_RING];
     unsigned int q_tail[ST_COUNT], q_head[ST_COUNT];
@@ -171,7 +172,9 @@ DE_DEV void q_push_group(WarpPool &p, uint32_t st, int slot, unsigned mask, int 
     if (lane == leader) atomicAdd(&p.q_avail[st], n);
 }
 // one-shot stages: every lane with a slot pushes it to stage PK_STAGE(npk); grouped per target stage
-DE_DEV void q_push_sorted(WarpPool &p, bool has, uint32_t st, int slot, int lane) {
+// (out of line on purpose: warp-collective, called converged from many sites -- inlined copies of the
+// queue code were 27 KB of the kernel and the instruction cache is the scarce resource here)
+__device__ __noinline__ void q_push_sorted(WarpPool &p, bool has, uint32_t st, int slot, int lane) {
     unsigned todo = __ballot_sync(0xFFFFFFFFu, has);
     while (todo) {
         int leader = __ffs(todo) - 1;
@@ -182,9 +185,9 @@ DE_DEV void q_push_sorted(WarpPool &p, bool has, uint32_t st, int slot, int lane
     }
 }
 // warp-collective: returns the number of slots obtained (<= want); lane i < n receives its slot
-DE_DEV int q_pop(WarpPool &p, uint32_t st, int want, int lane, int &slot) {
+__device__ __noinline__ int2 q_pop2(WarpPool &p, uint32_t st, int want, int lane) {
     unsigned int base = 0u;
-    int n = 0;
+    int n = 0, slot;
     if (lane == 0) {
         int a = atomicSub(&p.q_avail[st], want);
         n = a >= want ? want : (a > 0 ? a : 0);
@@ -202,7 +205,12 @@ DE_DEV int q_pop(WarpPool &p, uint32_t st, int want, int lane, int &slot) {
         do { e = r[pos & (WF_RING - 1)]; } while ((e >> 11) != tag);
         slot = (int)(e & 2047u);
     }
-    return n;
+    return make_int2(n, slot);
+}
+DE_DEV int q_pop(WarpPool &p, uint32_t st, int want, int lane, int &slot) {
+    int2 r = q_pop2(p, st, want, lane);
+    slot = r.y;
+    return r.x;
 }
 
 DE_DEV RngW load_rng(const Ctx &c, int slot, uint32_t pk) {
@@ -224,8 +232,11 @@ DE_DEV uint32_t setup_cloud_ratio(const Ctx &c, int slot, uint32_t pk, float3 o,
     float ts, tm;
     intersect_cloud_limits(o, d, c.pool.isect[slot], ts, tm);
     if (ts < tm) {
-        c.pool.t[slot] = ts; c.pool.tmax[slot] = tm;
-        return PK_SET_STAGE(pk, ST_CLOUD) | PK_RATIO;
+        float bound = cloud_density_bound(cloud_segment_cmax(c.s, o, d, ts, tm));
+        if (bound > 0.0f) {
+            c.pool.t[slot] = ts; c.pool.tmax[slot] = tm; c.pool.cmj[slot] = bound;
+            return PK_SET_STAGE(pk, ST_CLOUD) | PK_RATIO;
+        }
     }
     return PK_SET_STAGE(pk, ST_NEE_DONE);
 }
@@ -243,8 +254,11 @@ DE_DEV uint32_t setup_cloud_delta(const Ctx &c, int slot, uint32_t pk, float3 o,
     uint32_t rmo_ev = PK_RMO_EV(pk);
     float rmo_t = c.pool.aux[slot];
     if ((rmo_ev == kNullEvent || rmo_t > ts) && ts < tm) {
-        c.pool.t[slot] = ts; c.pool.tmax[slot] = tm;
-        return PK_SET_STAGE(pk, ST_CLOUD) & ~PK_RATIO;
+        float bound = cloud_density_bound(cloud_segment_cmax(c.s, o, d, ts, tm));
+        if (bound > 0.0f) {
+            c.pool.t[slot] = ts; c.pool.tmax[slot] = tm; c.pool.cmj[slot] = bound;
+            return PK_SET_STAGE(pk, ST_CLOUD) & ~PK_RATIO;
+        }
     }
     return finish_interaction(c, slot, pk, rmo_ev, rmo_t, PK_RMO_ID(pk));
 }
@@ -274,8 +288,12 @@ DE_DEV uint32_t setup_sdf(const Ctx &c, int slot, uint32_t pk, float3 o, float3 
     float ray_dist = 0.0f;
     float2 rd = rsi(o, d, kAtmosUpper);
     if (rd.x > 0.0f) ray_dist = rd.x;
-    c.pool.t[slot] = ray_dist;
     store_draw(c, slot, draw, 0u);
+    if (land_surely_missed(o + d * ray_dist, d, ray_dist, c.s.land_height_scale)) {  // exact: the march would return -1
+        c.pool.t[slot] = -1.0f;
+        return PK_SET_STAGE(pk, ST_SDF_DONE);
+    }
+    c.pool.t[slot] = ray_dist;
     return PK_SET_STAGE(pk, ST_SDF);
 }
 // top of the scatter loop (pathtracer.py:349-359)
@@ -440,7 +458,7 @@ template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int slot) {
         key1 = c.pool.pix[slot]; smp = c.pool.sample[slot];
         blk = ((c.pool.draw[slot] & 0xFFFFFFu) + 3u) >> 2;  // passes start on a block boundary; trips end on one
         o = ld_o(c, slot);
-        if (IS_CLOUD) { ext_cloud = cloud_ext_of(PK_SC(pk)); max_ext = ext_cloud * kCloudsDensity; }
+        if (IS_CLOUD) { ext_cloud = cloud_ext_of(PK_SC(pk)); max_ext = ext_cloud * c.pool.cmj[slot]; }
         else { const LambdaRow &lr = c.s.lam[PK_LAM(pk)]; ext = f3(lr.ext_r, lr.ext_m, lr.ext_o); max_ext = lr.max_ext_rmo; }
     };
     if (active) load();

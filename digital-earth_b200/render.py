@@ -1,0 +1,100 @@
+"""Headless renderer CLI: what `main.py` + the GGUI loop do, without a window.
+
+    python -m digital_earth_b200.render --config "config - florida.txt" --res 1920x1080 --spp 1024 \\
+        --textures synthetic:8192x4096 --out florida.png
+    torchrun --nproc-per-node 8 -m digital_earth_b200.render --config ... --orbit 120 --out-dir frames/
+
+One process per GPU.  A still frame is split by sample slice across ranks and sum-reduced with NCCL;
+an orbit (camera and look-at rotated about +Y, BASELINE configs[4]) is sharded by frame, no collective.
+"""
+import argparse
+import math
+import os
+import sys
+
+
+def orbit_config(cfg, angle_rad):
+    """Rotate camera position, look-at and up about the +Y (polar) axis."""
+    c, s = math.cos(angle_rad), math.sin(angle_rad)
+
+    def rot(v):
+        return (c * v[0] + s * v[2], v[1], -s * v[0] + c * v[2])
+    out = dict(cfg)
+    out["cam_pos"], out["look_at"], out["up"] = rot(cfg["cam_pos"]), rot(cfg["look_at"]), rot(cfg["up"])
+    return out
+
+
+def parse_textures(spec, scene_hint=""):
+    from . import textures
+    if spec.startswith("synthetic"):
+        w, h = (int(x) for x in (spec.split(":")[1] if ":" in spec else "2048x1024").split("x"))
+        stormy = "hurricane" in scene_hint
+        return textures.synthetic(w, h, cloud_cover=0.8 if stormy else 0.5, hurricane=stormy)
+    return textures.load_directory(spec)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--config", required=True, help="10-line scene file (earth_viewer.py:100-126,213-236)")
+    ap.add_argument("--res", default="1920x1080")
+    ap.add_argument("--spp", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=256, help="samples per launch")
+    ap.add_argument("--textures", default="textures", help="directory with the NASA maps, or synthetic:WxH")
+    ap.add_argument("--out", default=None, help="image file (default: screenshot/<main>-<timestamp>.jpg)")
+    ap.add_argument("--orbit", type=int, default=0, help="render N frames of an orbit instead of one still")
+    ap.add_argument("--degrees-per-frame", type=float, default=3.0)
+    ap.add_argument("--out-dir", default="frames")
+    ap.add_argument("--mode", default="wavefront", choices=["wavefront", "megakernel", "parity"])
+    ap.add_argument("--tonemapper", default="opendrt", choices=["opendrt", "agx"])
+    ap.add_argument("--save-accum", default=None, help=".npz checkpoint of the linear accumulation buffer + spp")
+    a = ap.parse_args(argv)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from . import Renderer, load_config, save_screenshot
+    from .distributed import frame_shard, reduce_accumulation, sample_slice
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, H = (int(x) for x in a.res.split("x"))
+    cfg = load_config(a.config)
+    r = Renderer((W, H), cfg["up"], textures=parse_textures(a.textures, a.config), device=local, mode=a.mode)
+    r.tonemapper = 1 if a.tonemapper == "agx" else 0
+    r.copy_textures()
+
+    def render_slice(first, n):
+        r.reset_framebuffer()
+        done = 0
+        while done < n:
+            k = min(a.batch, n - done)
+            r.accumulate(k, first_sample=first + done)
+            done += k
+
+    if a.orbit:
+        os.makedirs(a.out_dir, exist_ok=True)
+        for f in frame_shard(a.orbit, rank, world):
+            r.apply_config(orbit_config(cfg, math.radians(a.degrees_per_frame * f)))
+            render_slice(0, a.spp)
+            save_screenshot(r.fetch_image(spp=a.spp), os.path.join(a.out_dir, "frame_%04d.png" % f))
+    else:
+        r.apply_config(cfg)
+        first, n = sample_slice(a.spp, rank, world)
+        render_slice(first, n)
+        reduce_accumulation(r.color_buffer, dst=0)
+        if rank == 0:
+            img = r.fetch_image(spp=a.spp)
+            save_screenshot(img, a.out)
+            if a.save_accum:
+                np.savez_compressed(a.save_accum, accum=r.color_buffer.cpu().numpy(), spp=a.spp, config=np.array(list(map(str, cfg.items()))))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    r.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -142,8 +142,9 @@ def test_counters_and_flop_model_inputs(de, tex):
     assert c["segments"] >= c["paths"] and c["sdf_evals"] > 0 and c["rmo_steps"] > 0 and c["cloud_steps"] > 0
     orc, s = oracle_scene(de, tex, "florida")
     _, co = orc.render(s, 2, seed=r.seed)
-    for k in ("segments", "rmo_steps", "cloud_steps", "sdf_evals", "surface_hits"):
-        assert abs(c[k] - co[k]) <= 0.02 * co[k], (k, c[k], co[k])  # same paths up to fast-math branch flips
+    for k in ("segments", "rmo_steps", "sdf_evals", "surface_hits"):
+        assert abs(c[k] - co[k]) <= 0.1 * co[k], (k, c[k], co[k])  # same estimator: event rates agree statistically
+    assert c["cloud_steps"] <= 1.02 * co["cloud_steps"]  # local majorants only ever remove null collisions
     r.close()
 
 
@@ -155,3 +156,36 @@ def test_errors_are_reported_not_swallowed(de, tex):
     with pytest.raises(_lib.DeError):
         r.accumulate(0)
     r.close()
+
+
+@pytest.mark.parametrize("scene", ["Apollo 11", "florida", "sunset hurricane"])
+def test_product_flavour_converges_to_the_parity_flavour(de, tex, scene):
+    """BASELINE.json north_star image gate, GPU vs GPU: the product integrator (wavefront; FMA + MUFU
+    arithmetic, fitted atan2/asin, TEX-gather fetch, local cloud majorants -- so NOT the same paths any
+    more) against the IEEE source-order flavour that follows the oracle path by path, both at 4096 spp
+    with independent seeds.  Gate: relative RMSE < 1 % on the linear accumulation buffer (8x8 boxes, the
+    residual per-pixel Monte-Carlo noise at 4096 spp is ~3-10 %), mean radiance within 0.5 %, and a
+    box-level z-test using the two renders' own sample variance."""
+    spp, half = 4096, 2048
+    out = {}
+    for mode, seed in (("parity", 101), ("wavefront", 202)):
+        r = make(de, tex, scene, mode)
+        r.seed = seed
+        r.reset_framebuffer(); r.accumulate(half, first_sample=0)
+        first = r.color_buffer.cpu().numpy().copy()
+        r.accumulate(half, first_sample=half)
+        total = r.color_buffer.cpu().numpy().copy()
+        out[mode] = (first / half, (total - first) / half, total / spp)
+        r.close()
+    box = lambda a: a.reshape(H // 8, 8, W // 8, 8, 3).mean((1, 3))  # noqa: E731
+    pa, pb, pm = (box(x) for x in out["parity"])
+    wa, wb, wm = (box(x) for x in out["wavefront"])
+    assert abs(wm.mean() - pm.mean()) < 0.005 * pm.mean(), (wm.mean(), pm.mean())
+    rel_rmse = np.sqrt(np.mean((wm - pm) ** 2)) / np.mean(pm)
+    assert rel_rmse < 0.01, rel_rmse
+    # variance of a box mean from the two independent halves of each render: var(mean) ~ (a-b)^2/4
+    var = ((pa - pb) ** 2 + (wa - wb) ** 2) / 4.0
+    lit = pm.sum(-1) > 1e-4
+    z = ((wm - pm) / np.sqrt(var + 1e-16))[lit]
+    assert abs(np.median(z)) < 0.3, np.median(z)
+    assert np.mean(np.abs(z) > 6.0) < 0.05, np.mean(np.abs(z) > 6.0)

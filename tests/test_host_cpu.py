@@ -177,3 +177,25 @@ def test_oracle_multithreaded_render_is_deterministic():
     b, _ = orc.render(s, 1, first_sample=0, nthreads=4)
     c, _ = orc.render(s, 1, first_sample=1, nthreads=4)
     assert np.allclose(b + c, a1, rtol=1e-6, atol=1e-9)  # sample slices add up (multi-GPU partition property)
+
+
+def test_orbit_rotates_about_the_polar_axis():
+    from digital_earth_b200.render import orbit_config
+    cfg = de.load_config(os.path.join(CFG, "config - florida.txt"))
+    o = orbit_config(cfg, np.radians(90.0))
+    assert abs(np.linalg.norm(o["cam_pos"]) - np.linalg.norm(cfg["cam_pos"])) < 1e-3
+    assert abs(o["cam_pos"][1] - cfg["cam_pos"][1]) < 1e-9            # latitude kept
+    assert abs(np.dot(o["cam_pos"], cfg["cam_pos"]) - cfg["cam_pos"][1] ** 2) < 1e-3 * np.linalg.norm(cfg["cam_pos"]) ** 2  # 90 deg in the equatorial plane
+    back = orbit_config(o, np.radians(-90.0))
+    assert np.allclose(back["cam_pos"], cfg["cam_pos"]) and np.allclose(back["look_at"], cfg["look_at"])
+
+
+def test_lut_provenance(luts):
+    """The packed LUTs are byte-identical to what the reference's own generator scripts produce
+    (verdict recorded by tests/golden/check_lut_provenance.py) and unchanged since (sha256)."""
+    import hashlib
+    import json
+    prov = json.load(open(os.path.join(ROOT, "tests", "golden", "lut_provenance.json")))
+    assert prov["ozone_regenerated_bit_exact"] and prov["srgb2spec_regenerated_bit_exact"]
+    for k in ("cie", "srgb2spec", "o3", "crf"):
+        assert hashlib.sha256(np.ascontiguousarray(luts[k]).tobytes()).hexdigest() == prov["sha256_" + k], k
