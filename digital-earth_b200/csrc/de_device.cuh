@@ -253,6 +253,16 @@ DE_DEV float2 sphere_uv(float3 pos) {
     uv.y = uv.y - floorf(uv.y);
     return uv;
 }
+#if !DE_EXACT
+// product flavour: position + its 1/|pos| (the caller already needs r), no second normalisation.
+// u, v come out in [0,1]; the fract() of math_utils.py:44 only matters at the exact pole / date line
+// (measure zero) and the clamp address mode keeps the fetch in range there.
+DE_DEV float sample_sphere_r8_inv(const DevTex &t, float3 pos, float inv_r) {
+    float u = fmaf(fast_atan2(pos.z, -pos.x), 0.5f / kPi, 0.5f);
+    float v = fmaf(fast_asin(pos.y * inv_r), 1.0f / kPi, 0.5f);
+    return tex_r8(t, u, v);
+}
+#endif
 DE_DEV float sample_sphere_r8(const DevTex &t, float3 pos) { float2 uv = sphere_uv(pos); return tex_r8(t, uv.x, uv.y); }
 DE_DEV float3 sample_sphere_rgb8(const DevTex &t, float3 pos) { float2 uv = sphere_uv(pos); return tex_rgb8(t, uv.x, uv.y); }
 #if !DE_EXACT

@@ -417,7 +417,8 @@ template <bool COUNT> DE_DEV void burst_sdf(Ctx &c, int slot) {
         if (active) {
             float3 ro = o + d * t;
             DE_COUNT(c.cn, C_SDF); DE_COUNT(c.cn, C_TEX);
-            float dist = length(ro) - kPlanetR - scale * sample_sphere_r8(c.s.tex[1], ro);
+            float r2 = dot(ro, ro), inv_r = rsqrtf(r2);
+            float dist = r2 * inv_r - kPlanetR - scale * sample_sphere_r8_inv(c.s.tex[1], ro, inv_r);
             t += dist;
             ++iter;
             if (t > 63710000.0f || fabsf(dist) < t * 0.0001f || iter >= 250u) {
@@ -449,7 +450,7 @@ template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int slot) {
     const uint32_t ST_SELF = IS_CLOUD ? ST_CLOUD : ST_RMO;
     bool active = slot >= 0;
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1), ext = f3(0, 0, 0);
-    float t = 0.0f, tmax = 0.0f, T = 1.0f, max_ext = 1.0f, ext_cloud = 0.0f;
+    float t = 0.0f, tmax = 0.0f, T = 1.0f, max_ext = 1.0f, inv_max = 1.0f, ext_cloud = 0.0f;
     uint32_t pk = 0u, blk = 0u, key1 = 0u, smp = 0u;
     auto load = [&]() {
         d = ld_d(c, slot);
@@ -460,6 +461,7 @@ template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int slot) {
         o = ld_o(c, slot);
         if (IS_CLOUD) { ext_cloud = cloud_ext_of(PK_SC(pk)); max_ext = ext_cloud * c.pool.cmj[slot]; }
         else { const LambdaRow &lr = c.s.lam[PK_LAM(pk)]; ext = f3(lr.ext_r, lr.ext_m, lr.ext_o); max_ext = lr.max_ext_rmo; }
+        inv_max = 1.0f / max_ext;
     };
     if (active) load();
     const int min_active = min(WF_MIN_ACTIVE, (__popc(__ballot_sync(full, active)) + 1) / 2);
@@ -474,13 +476,20 @@ template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int slot) {
             uint32_t ev = 0u, id = IS_CLOUD ? 3u : 0u, draw_after = 0u;
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
-                t += -logf(u32_to_unit(h ? rb.z : rb.x)) / max_ext;
+                t -= __logf(u32_to_unit(h ? rb.z : rb.x)) * inv_max;
                 const float3 pos = o + d * t;  // from the origin every time: independent of where bursts were cut
                 if (t >= tmax) { done = true; draw_after = 4u * blk + 2u * h + 1u; break; }
                 float es0 = 0.0f, es1 = 0.0f, es2 = 0.0f, sum;
-                if (IS_CLOUD) {
+                if (IS_CLOUD) {  // get_clouds_density (pathtracer.py:48-65) with one shared rsqrt
                     DE_COUNT(c.cn, C_CLOUD);
-                    sum = ext_cloud * get_clouds_density<COUNT>(c.s, pos, c.cn);
+                    float r2 = dot(pos, pos), inv_r = rsqrtf(r2), r = r2 * inv_r, dens = 0.0f;
+                    if (r > kCloudsLower && r < kCloudsUpper) {
+                        DE_COUNT(c.cn, C_TEX);
+                        float hgt = (r - kCloudsLower) * (1.0f / kCloudsThickness);
+                        float cl = sample_sphere_r8_inv(c.s.tex[3], pos, inv_r);
+                        dens = (hgt - 0.2f < cl * 0.8f && 0.2f - hgt < cl * 0.2f) ? fmaxf(cl, 0.4f) : 0.0f;
+                    }
+                    sum = ext_cloud * (dens * kCloudsDensity);
                 } else {
                     DE_COUNT(c.cn, C_RMO);
                     float3 dens = get_density(get_elevation(pos));
@@ -488,16 +497,16 @@ template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int slot) {
                     sum = (es0 + es1) + es2;
                 }
                 if (ratio) {
-                    T *= 1.0f - sum / max_ext;
+                    T *= 1.0f - sum * inv_max;
                     if (T < 1e-5f) { done = true; draw_after = 4u * blk + 2u * h + 2u; break; }
                 } else {
                     float rand = u32_to_unit(h ? rb.w : rb.y);
-                    if (rand < sum / max_ext) {
+                    if (rand < sum * inv_max) {
                         if (!IS_CLOUD) {
                             float cmf = es0;
-                            if (!(rand < cmf / max_ext)) {
+                            if (!(rand < cmf * inv_max)) {
                                 id = 1u; cmf += es1;
-                                if (!(rand < cmf / max_ext)) { id = 2u; cmf += es2; if (!(rand < cmf / max_ext)) id = 3u; }
+                                if (!(rand < cmf * inv_max)) { id = 2u; cmf += es2; if (!(rand < cmf * inv_max)) id = 3u; }
                             }
                         }
                         ev = 1u; done = true; draw_after = 4u * blk + 2u * h + 3u;  // the slot before draw_after decides scatter vs absorb
