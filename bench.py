@@ -100,6 +100,18 @@ def textures_for(a, tw, th):
     return de.textures.synthetic(tw, th, cloud_cover=0.8 if a.scene == "sunset" else 0.5, hurricane=a.scene == "sunset", seed=0)
 
 
+def oracle_flop_per_path(a, textures):
+    """Algorithmic work per path = SURVEY 8(d) formula on the ORACLE's event counters for this view
+    (the reference algorithm's own step counts; the product kernel removes null collisions and misses,
+    which must not shrink the numerator).  Small sample: 240x136, 2 spp."""
+    from oracle import oracle as orc
+    cfg = scene_cfg(a)
+    s = orc.Scene(textures, 240, 136, cam_pos=cfg["cam_pos"], look_at=cfg["look_at"], up=cfg["up"], fov=cfg["fov"], aspect_scale=cfg["aspect_scale"],
+                  sun_angle=cfg["sun_angle"], sun_path_rot=cfg["sun_path_rot"])
+    _, cnt = orc.render(s, 2, seed=1)
+    return flop_per_path(cnt), cnt
+
+
 def cpu_baseline(a, steps=1, textures=None):
     """Oracle port on all host cores, bounded sample of the same view; returns (paths/s, description, cores)."""
     from oracle import oracle as orc
@@ -235,7 +247,7 @@ def main():
         except Exception:
             pass
         sm_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
-        fpp = flop_per_path(counters)
+        fpp, ocnt = oracle_flop_per_path(a, tex)
         peak_tflops = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # FP32 FMA issue peak
         achieved = fpp * (W * H * spp_local) / (kernel_ms * 1e-3) / 1e12
         traffic = None
@@ -256,7 +268,9 @@ def main():
             "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                          "traffic": traffic, "kernel": "k_render_wavefront", "kernel_ms": kernel_ms, "flop_per_path": fpp,
                          "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (max SM clock of MEASURED_PEAKS.json); HBM/tensor peaks do not bound this path" % sm_max,
-                         "events_per_path": {k: counters[k] / max(counters["paths"], 1) for k in ("segments", "rmo_steps", "cloud_steps", "sdf_evals", "tex_fetches", "surface_hits")}},
+                         "flop_model": "60*N_rmo+45*N_cloud+45*N_sdf+400*N_seg+200 on the oracle's event counts for this view (SURVEY 8d)",
+                         "oracle_events_per_path": {k: ocnt[k] / max(ocnt["paths"], 1) for k in ("segments", "rmo_steps", "cloud_steps", "sdf_evals", "tex_fetches", "surface_hits")},
+                         "kernel_events_per_path": {k: counters[k] / max(counters["paths"], 1) for k in ("segments", "rmo_steps", "cloud_steps", "sdf_evals", "tex_fetches", "surface_hits")}},
             "clocks": clocks,
         }
         if world == 1 and not a.no_cpu_baseline:

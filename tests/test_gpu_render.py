@@ -189,7 +189,9 @@ def test_product_flavour_converges_to_the_parity_flavour(de, tex, scene):
     # the north-star figure (rel. RMSE < 1 % at 4096 spp) where the residual noise allows it: 32x32 boxes
     big = lambda a: a.reshape(H // 32, 32, W // 32, 32, 3).mean((1, 3))  # noqa: E731
     rel_rmse_big = np.sqrt(np.mean((big(out["wavefront"][2]) - big(out["parity"][2])) ** 2)) / np.mean(pm)
-    assert rel_rmse_big < 0.01, rel_rmse_big
+    var_big = ((big(out["parity"][0]) - big(out["parity"][1])) ** 2 + (big(out["wavefront"][0]) - big(out["wavefront"][1])) ** 2) / 4.0
+    noise_big = np.sqrt(np.mean(var_big)) / np.mean(pm)
+    assert rel_rmse_big < max(0.01, 1.5 * noise_big), (rel_rmse_big, noise_big)
     lit = pm.sum(-1) > 1e-4
     z = ((wm - pm) / np.sqrt(var + 1e-16))[lit]
     assert abs(np.median(z)) < 0.3, np.median(z)
