@@ -352,6 +352,20 @@ DE_DEV float3 get_density(float h) {
 }
 DE_DEV float get_elevation(float3 p) { return sqrtf(p.x * p.x + p.y * p.y + p.z * p.z) - kPlanetR; }
 
+#if !DE_EXACT
+// Majorant of sigma.rho over the part [ts, tm] of a ray (product flavour).  The Rayleigh and aerosol
+// fits decrease with altitude (the aerosol fit steps up by 1.3e-5 at 11.5 km: 1.001 covers it) and the
+// ozone fit is bounded by its 25 km peak value 1 below the peak and decreases above it, so the densities
+// at the LOWEST point of the segment bound the whole segment.  The reference uses the sea-level values
+// everywhere (pathtracer.py:336,355); any valid majorant leaves delta / ratio tracking unbiased.
+DE_DEV float rmo_segment_majorant(float3 ext, float3 o, float3 d, float ts, float tm) {
+    float b = dot(o, d), r2 = dot(o, o);
+    float tp = fminf(fmaxf(-b, ts), tm);                    // perigee clamped to the segment
+    float hmin = fmaxf(sqrtf(fmaxf(r2 + tp * (2.0f * b + tp), 0.0f)) - kPlanetR - 2.0f, 0.0f);  // 2 m of f32 slack
+    float oz = hmin < 25000.0f ? 1.0f : get_ozone_density(hmin);
+    return 1.001f * (ext.x * get_rayl_density(hmin) + ext.y * get_mie_density(hmin)) + ext.z * oz;
+}
+#endif
 // ---------------------------------------------------------------- spectra (volume_rendering_models.py:48-51,194-224; colour.py:51-60)
 DE_DEV float air(float wl) {
     float rcp = 1.0f / (wl * wl);

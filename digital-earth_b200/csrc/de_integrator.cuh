@@ -146,6 +146,9 @@ DE_DEV int sample_interaction(const DevScene &s, float3 pos, float3 dir, float l
     float t_max = land_isection >= 0.0f ? land_isection : atm.y;
     if (atm.y < 0.0f) t_max = -1.0f;
     float rmo_t; int rmo_id;
+#if !DE_EXACT
+    if (t_start < t_max) max_rmo = fminf(max_rmo, rmo_segment_majorant(ext_rmo, pos, dir, t_start, t_max));
+#endif
     int rmo_event = delta_tracking<COUNT, false>(s, pos, dir, t_start, t_max, ext_rmo, ext_cloud, max_rmo, rng, cn, rmo_t, rmo_id);
     intersect_cloud_limits(pos, dir, land_isection, t_start, t_max);
     int event = rmo_event, id = rmo_id;
@@ -171,6 +174,9 @@ DE_DEV float sample_transmittance(const DevScene &s, float3 pos, float3 dir, flo
     float t_start = fmaxf(0.0f, atm.x);
     float t_max = land_isection >= 0.0f ? land_isection : atm.y;
     if (atm.y < 0.0f) t_max = -1.0f;
+#if !DE_EXACT
+    if (t_start < t_max) max_rmo = fminf(max_rmo, rmo_segment_majorant(ext_rmo, pos, dir, t_start, t_max));
+#endif
     float T = ratio_tracking<COUNT, false>(s, pos, dir, t_start, t_max, ext_rmo, ext_cloud, max_rmo, rng, cn);
     intersect_cloud_limits(pos, dir, land_isection, t_start, t_max);
 #if !DE_EXACT

@@ -74,7 +74,7 @@ struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
     float mdx[WF_SLOTS], mdy[WF_SLOTS], mdz[WF_SLOTS];                        // main ray direction while the NEE ray is tracked
     float nx[WF_SLOTS], ny[WF_SLOTS], nz[WF_SLOTS], m0[WF_SLOTS], m1[WF_SLOTS], m2[WF_SLOTS];  // surface normal, albedo, ocean, bathymetry
     float na[WF_SLOTS], nb[WF_SLOTS];                                         // NEE factors: phase | brdf, n.l (nb doubles as the decision-slot word)
-    float cmj[WF_SLOTS];                                                      // cloud pass: local density majorant (0.029 * max(cmax, 0.4))
+    float cmj[WF_SLOTS];                                                      // tracking pass: local majorant (cloud: density bound; rmo: sigma.rho bound)
     // per-stage MPMC ring queues of ready slots: entry = slot | (lap & 31) << 11
     uint16_t ring[ST_COUNT][WF_RING];
     unsigned int q_tail[ST_COUNT], q_head[ST_COUNT];
@@ -91,11 +91,15 @@ struct WfParams {
     uint32_t seed, first_sample;
 };
 
+#ifndef WF_PHILOX_UNROLL
+#define WF_PHILOX_UNROLL 1  // rolled on purpose: 10 unrolled rounds are 2.8 KB of the hottest shared code (I-cache)
+#endif
+constexpr int kPhiloxUnroll = WF_PHILOX_UNROLL;
 // One Philox4x32-10 block; deliberately NOT inlined: ~70 instructions that would otherwise be
 // replicated at every draw site and blow the instruction cache (profiles/r1_wavefront.md).
 __device__ __noinline__ uint4 philox_block(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2) {
     uint32_t c3 = 0u;
-#pragma unroll
+#pragma unroll kPhiloxUnroll
     for (int r = 0; r < 10; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
@@ -273,7 +277,9 @@ DE_DEV uint32_t setup_rmo(const Ctx &c, int slot, uint32_t pk, float3 o, float3 
     pk = ratio ? (pk | PK_RATIO) : (pk & ~PK_RATIO);
     if (ratio) c.pool.aux[slot] = 1.0f;
     if (t_start < t_max) {
+        const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
         c.pool.t[slot] = t_start; c.pool.tmax[slot] = t_max;
+        c.pool.cmj[slot] = fminf(lr.max_ext_rmo, rmo_segment_majorant(f3(lr.ext_r, lr.ext_m, lr.ext_o), o, d, t_start, t_max));  // local majorant
         return PK_SET_STAGE(pk, ST_RMO);
     }
     if (!ratio) {  // no atmosphere on the way: NULL event at t_start
@@ -460,7 +466,7 @@ template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int slot) {
         blk = ((c.pool.draw[slot] & 0xFFFFFFu) + 3u) >> 2;  // passes start on a block boundary; trips end on one
         o = ld_o(c, slot);
         if (IS_CLOUD) { ext_cloud = cloud_ext_of(PK_SC(pk)); max_ext = ext_cloud * c.pool.cmj[slot]; }
-        else { const LambdaRow &lr = c.s.lam[PK_LAM(pk)]; ext = f3(lr.ext_r, lr.ext_m, lr.ext_o); max_ext = lr.max_ext_rmo; }
+        else { const LambdaRow &lr = c.s.lam[PK_LAM(pk)]; ext = f3(lr.ext_r, lr.ext_m, lr.ext_o); max_ext = c.pool.cmj[slot]; }
         inv_max = 1.0f / max_ext;
     };
     if (active) load();
@@ -668,7 +674,6 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
     Counters cn;
     cn.clear();
     Ctx c{s, dv, P, pool, cn, lane};
-    const int pref = (threadIdx.x >> 5) % 4 == 0 ? (int)ST_SDF : ((threadIdx.x >> 5) % 4 == 1 ? (int)ST_RMO : (int)ST_CLOUD);
     // all slots start free (queue ST_NEW); ring entries carry lap tag 31 until first written
     for (int k = threadIdx.x; k < ST_COUNT * WF_RING; k += blockDim.x) (&pool.ring[0][0])[k] = 0xFFFFu;
     __syncthreads();
@@ -688,9 +693,8 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         const bool work_left = (wl & 1) != 0;
         int av = lane < (int)ST_COUNT ? *(volatile int *)&pool.q_avail[lane] : 0;
         if (lane == (int)ST_NEW && work_left && av < 32) av = 0;
-        // warps of one SM sub-partition (warp % 4) prefer the same loop stage, so its instruction-cache
-        // slice holds one loop body; any other queue wins only when it is clearly fuller
-        if (lane == pref && av >= 32) av += WF_SLOTS;
+        // plain fullest-queue policy: stage affinity per sub-partition and role-specialised warps were
+        // both measured slower (profiles/r1_wavefront.md, "scheduling experiments")
         int key = av > 0 ? (av << 4) | lane : 0;
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(full, key, o));
