@@ -656,7 +656,7 @@ DE_DEV void spectrum_sample(const float *cie, float sample, float &wavelength, f
 // Same bisection on the precomputed thresholds cdf[j] = saturate(mean CIE CDF(j/512)); returns j (mid = j/512).
 DE_DEV int spectrum_bin(const float *cdf, float sample) {
     int lo = 0, hi = 512, mid = 256;
-#pragma unroll
+#pragma unroll 1
     for (int x = 0; x < 8; ++x) {
         float val = cdf[mid];
         if (val < sample) lo = mid;

@@ -35,6 +35,9 @@ namespace de_fast {
 #ifndef WF_MIN_ACTIVE
 #define WF_MIN_ACTIVE 20  // a burst ends when fewer lanes than this are busy and the queue is dry
 #endif
+#ifndef WF_STICKY
+#define WF_STICKY 64
+#endif
 #ifndef WF_REFILL_MIN
 #define WF_REFILL_MIN 6  // idle lanes that trigger a mid-burst refill
 #endif
@@ -139,6 +142,29 @@ __device__ __noinline__ float3 fetch_rgb8_ool(const uint8_t *data, int w, int h,
     DevTex t; t.data = data; t.w = w; t.h = h; t.c = 3; t.obj = 0;
     return sample_sphere_rgb8(t, f3(px, py, pz));
 }
+// cold, large bodies shared by the one-shot stages (kept out of line for the instruction cache)
+__device__ __noinline__ float2 brdf_ool(float albedo, float ocean, float bathy, float vx, float vy, float vz, float nx, float ny, float nz, float lx, float ly, float lz) {
+    float ndl;
+    float b = earth_brdf(albedo, ocean, bathy, f3(vx, vy, vz), f3(nx, ny, nz), f3(lx, ly, lz), ndl);
+    return make_float2(b, ndl);
+}
+__device__ __noinline__ float phase_eval_ool(float ax, float ay, float az, float bx, float by, float bz, int id, bool reduce) {
+    return evaluate_phase(f3(ax, ay, az), f3(bx, by, bz), id, reduce);
+}
+struct BlockRng {  // up to four draws from one Philox block, static order
+    uint4 b; int i;
+    DE_DEV float next() { uint32_t v = i == 0 ? b.x : (i == 1 ? b.y : (i == 2 ? b.z : b.w)); ++i; return u32_to_unit(v); }
+    DE_DEV void align() {}
+};
+// sample_phase (pathtracer.py:249-261) on one Philox block; returns (dir, phase/pdf) and the number of words used in .w of the int
+__device__ __noinline__ float4 phase_sample_ool(float dx, float dy, float dz, int id, bool reduce, uint4 blk, int *used) {
+    BlockRng r{blk, 0};
+    float pdp;
+    float3 d = sample_phase(f3(dx, dy, dz), id, reduce, r, pdp);
+    *used = r.i;
+    return make_float4(d.x, d.y, d.z, pdp);
+}
+__device__ __noinline__ float2 sphere_uv_ool(float px, float py, float pz) { return sphere_uv(f3(px, py, pz)); }
 DE_DEV float r8_ool(const DevTex &t, float3 p) { return fetch_r8_ool(t.data, t.w, t.h, p.x, p.y, p.z); }
 DE_DEV float3 rgb8_ool(const DevTex &t, float3 p) { return fetch_rgb8_ool(t.data, t.w, t.h, p.x, p.y, p.z); }
 
@@ -163,7 +189,15 @@ DE_DEV void q_push(WarpPool &p, uint32_t st, int slot) {
     atomicAdd(&p.q_avail[st], 1);
 }
 // warp-aggregated push of the lanes in `mask` (all to stage st): one reservation for the group
-DE_DEV void q_push_group(WarpPool &p, uint32_t st, int slot, unsigned mask, int lane) {
+#ifndef WF_PUSHGROUP_INLINE
+#define WF_PUSHGROUP_INLINE 1  // measured: out of line costs 4 % (it is called under divergence)
+#endif
+#if WF_PUSHGROUP_INLINE
+DE_DEV
+#else
+__device__ __noinline__
+#endif
+void q_push_group(WarpPool &p, uint32_t st, int slot, unsigned mask, int lane) {
     int n = __popc(mask), leader = __ffs(mask) - 1;
     unsigned int base = 0u;
     if (lane == leader) base = atomicAdd(&p.q_tail[st], (unsigned)n);
@@ -451,7 +485,14 @@ template <bool COUNT> DE_DEV void burst_sdf(Ctx &c, int slot) {
 // (words 0,1 and 2,3: free flight + acceptance test; a ratio step leaves its second word unused),
 // so the RNG is issued converged with static word selection.  A real collision only records the
 // slot of its scatter/absorb draw (pathtracer.py:270); ST_EVENT evaluates it for the winner.
+#ifndef WF_TRACK_TEMPLATE
+#define WF_TRACK_TEMPLATE 0
+#endif
+#if WF_TRACK_TEMPLATE
 template <bool COUNT, bool IS_CLOUD> DE_DEV void burst_track(Ctx &c, int slot) {
+#else
+template <bool COUNT> DE_DEV void burst_track(Ctx &c, int slot, const bool IS_CLOUD) {  // IS_CLOUD is warp-uniform: one copy of the loop
+#endif
     const unsigned full = 0xFFFFFFFFu;
     const uint32_t ST_SELF = IS_CLOUD ? ST_CLOUD : ST_RMO;
     bool active = slot >= 0;
@@ -581,7 +622,7 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
     if (ev == (uint32_t)kScatterEvent) {
         float3 ipos = o + d * c.pool.t[slot];
         bool blocked = rsi(ipos, light_dir, kPlanetR).y > 0.0f;
-        c.pool.na[slot] = evaluate_phase(d, light_dir, (int)id, sc > 0u);
+        c.pool.na[slot] = phase_eval_ool(d.x, d.y, d.z, light_dir.x, light_dir.y, light_dir.z, (int)id, sc > 0u);
         c.pool.mdx[slot] = d.x; c.pool.mdy[slot] = d.y; c.pool.mdz[slot] = d.z;
         st_o(c, slot, ipos); st_d(c, slot, light_dir);
         pk = PK_SET_ID(pk, id) & ~PK_SURFACE;
@@ -609,9 +650,8 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
         float albedo = lr.s2s_valid != 0.0f ? dot(m.albedo_srgb, f3(lr.s2s_r, lr.s2s_g, lr.s2s_b)) : 0.0f;
         c.pool.L[slot] += c.pool.thr[slot] * m.emissive * lr.nightlights_power;
         float3 offset_pos = land_pos * (1.0f + 0.0001f * c.s.land_height_scale / 12000.0f);
-        float ndl;
-        float dbrdf = earth_brdf(albedo, m.ocean, m.bathymetry, -d, nrm, light_dir, ndl);
-        c.pool.na[slot] = dbrdf; c.pool.nb[slot] = ndl;
+        float2 bn = brdf_ool(albedo, m.ocean, m.bathymetry, -d.x, -d.y, -d.z, nrm.x, nrm.y, nrm.z, light_dir.x, light_dir.y, light_dir.z);
+        c.pool.na[slot] = bn.x; c.pool.nb[slot] = bn.y;
         c.pool.nx[slot] = nrm.x; c.pool.ny[slot] = nrm.y; c.pool.nz[slot] = nrm.z;
         c.pool.m0[slot] = albedo; c.pool.m1[slot] = m.ocean; c.pool.m2[slot] = m.bathymetry;
         c.pool.mdx[slot] = d.x; c.pool.mdy[slot] = d.y; c.pool.mdz[slot] = d.z;
@@ -638,15 +678,17 @@ template <bool COUNT> DE_DEV uint32_t stage_nee_done(Ctx &c, int slot) {
         float3 nrm = f3(c.pool.nx[slot], c.pool.ny[slot], c.pool.nz[slot]);
         rng.align();
         nd = sample_hemisphere_cosine_weighted(nrm, rng);
-        float unused;
-        float brdf = earth_brdf(c.pool.m0[slot], c.pool.m1[slot], c.pool.m2[slot], -main_d, nrm, nd, unused);
+        float brdf = brdf_ool(c.pool.m0[slot], c.pool.m1[slot], c.pool.m2[slot], -main_d.x, -main_d.y, -main_d.z, nrm.x, nrm.y, nrm.z, nd.x, nd.y, nd.z).x;
         thr *= brdf * kPi;
     } else {
         Lacc += thr * T * lr.sun_irradiance * c.pool.na[slot];
-        float pdp;
         rng.align();
-        nd = sample_phase(main_d, (int)PK_ID(pk), sc > 0u, rng, pdp);
-        thr *= pdp;
+        uint4 blk = philox_block(rng.key0, rng.key1, rng.sample, rng.bounce, rng.draw >> 2);
+        int used = 0;
+        float4 sp = phase_sample_ool(main_d.x, main_d.y, main_d.z, (int)PK_ID(pk), sc > 0u, blk, &used);
+        nd = f3(sp.x, sp.y, sp.z);
+        thr *= sp.w;
+        rng.b0 = blk.x; rng.b1 = blk.y; rng.b2 = blk.z; rng.b3 = blk.w; rng.valid = true; rng.draw += (uint32_t)used;  // the roulette draw follows in the same block
     }
     c.pool.L[slot] = Lacc;
     bool terminate = false;
@@ -685,6 +727,7 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
     }
     if (threadIdx.x == 0) { pool.retired = 0; pool.work_left = 1; }
     __syncthreads();
+    int last_st = -1;
     for (;;) {
         // 1. pick the fullest stage queue (free slots only count in whole chunks of 32 while work remains)
         int wl = 0;
@@ -696,6 +739,9 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         // plain fullest-queue policy: stage affinity per sub-partition and role-specialised warps were
         // both measured slower (profiles/r1_wavefront.md, "scheduling experiments")
         int key = av > 0 ? (av << 4) | lane : 0;
+#if WF_STICKY
+        if (lane == last_st && av >= WF_STICKY) key += 1 << 20;  // stay on the stage whose code is warm while it has a full group
+#endif
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(full, key, o));
         key = __shfl_sync(full, key, 0);
@@ -705,14 +751,19 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
             continue;
         }
         const uint32_t st = (uint32_t)(key & 15);
+        last_st = (int)st;
         // 2. take up to 32 ready slots
         int slot;
         int n = q_pop(pool, st, 32, lane, slot);
         if (n == 0) continue;
         // 3. run the stage
         if (st == ST_SDF) burst_sdf<COUNT>(c, slot);
+#if WF_TRACK_TEMPLATE
         else if (st == ST_RMO) burst_track<COUNT, false>(c, slot);
         else if (st == ST_CLOUD) burst_track<COUNT, true>(c, slot);
+#else
+        else if (st == ST_RMO || st == ST_CLOUD) burst_track<COUNT>(c, slot, st == ST_CLOUD);
+#endif
         else {
             uint32_t npk = 0u;
             bool has = slot >= 0;
