@@ -52,6 +52,7 @@ _SIGS = {
     "de_sync": ([_P], _I),
     "de_get_counters": ([_P, C.POINTER(DeCounters)], _I),
     "de_set_counting": ([_P, _I], _I),
+    "de_get_stage_profile": ([_P, _P], _I),
     "de_test_philox": ([_P, _P, _P, _I], _I),
     "de_test_rsi": ([_P, _P, _P, _P, _P, _I], _I),
     "de_test_density": ([_P, _P, _P, _I], _I),

@@ -144,6 +144,13 @@ int de_set_mode(de_ctx *ctx, int mode) {
     ctx->mode = mode;
     return DE_OK;
 }
+int de_get_stage_profile(de_ctx *ctx, uint64_t *out32) {
+    ENTER();
+    NEED(out32, "out is NULL");
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->wf) return fail(ctx, DE_ERR_STATE, "the wavefront integrator has not run yet");
+    return de_wavefront_profile(ctx->wf, (unsigned long long *)out32) == 0 ? DE_OK : fail(ctx, DE_ERR_CUDA, "profile copy failed");
+}
 int de_set_counting(de_ctx *ctx, int enabled) {
     ENTER();
     ctx->counting = enabled != 0;

@@ -324,6 +324,28 @@ DE_DEV bool land_surely_missed(float3 p, float3 dir, float s0, float scale) {
     float need = kPlanetR + scale + 1e-4f * (s0 + fmaxf(-b, 0.0f)) + 100.0f;
     return rmin2 > need * need;
 }
+// Same argument at an iterate of the march (s = distance travelled so far): above every terrain by more
+// than the stopping tolerance can still reach, and receding => the reference's loop can only run off to
+// 10 R and return -1.
+DE_DEV bool march_surely_missed(float3 ro, float3 dir, float r2, float s, float scale) {
+    float need = kPlanetR + scale + 1e-4f * s + 100.0f;
+    return r2 > need * need && dot(ro, dir) > 0.0f;
+}
+// Nothing can be hit above the terrain-top sphere R+scale: distance from p (s0 already travelled) to that
+// sphere if p is outside and the ray enters it, else 0.  The reference's iterates from the atmosphere top
+// stop at the first one within 1e-4*t of the surface, so WHERE inside that band the march stops depends on
+// the iterate sequence; skipping the approach changes it.  The skip is therefore only taken when the band
+// is at most 400 m (t <= 4e6 m: low orbits, secondary rays); far cameras (Apollo: band 5.7 km) keep the
+// reference's iterates exactly.
+DE_DEV float skip_to_terrain_top(float3 p, float3 dir, float s0, float scale) {
+    const float Rg = kPlanetR + scale + 16.0f;
+    float b = dot(p, dir), r = sqrtf(dot(p, p));
+    if (r <= Rg || b >= 0.0f) return 0.0f;
+    float disc = b * b - (r - Rg) * (r + Rg);
+    if (!(disc > 0.0f)) return 0.0f;
+    float skip = fmaxf(-b - sqrtf(disc), 0.0f);
+    return s0 + skip <= 4.0e6f ? skip : 0.0f;
+}
 #endif
 // ---------------------------------------------------------------- medium densities (volume_rendering_models.py:229-277)
 DE_DEV float get_ozone_density(float h) {
@@ -407,6 +429,14 @@ DE_DEV float draine_phase(float c, float g, float a) {
 }
 struct CloudPar { float g_hg, g_draine, alpha_draine, w_draine; };
 DE_DEV CloudPar cloud_params(bool reduce_peak) {
+#if !DE_EXACT
+    {   // droplet size is the constant 8 (volume_rendering_models.py:155): fold the four exps (product flavour)
+        CloudPar q;
+        q.g_hg = reduce_peak ? 0.91f : 0.98446935f;
+        q.g_draine = 0.54106367f; q.alpha_draine = 20.325685f; q.w_draine = 0.47364232f;
+        return q;
+    }
+#endif
     const float d = 8.0f;
     CloudPar p;
     p.g_hg = reduce_peak ? 0.91f : expf(-0.0990567f / (d - 1.67154f));

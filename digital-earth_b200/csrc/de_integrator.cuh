@@ -27,9 +27,13 @@ template <bool COUNT> DE_DEV float intersect_land(const DevScene &s, float3 pos,
     if (rd.x > 0.0f) ray_dist = rd.x;
 #if !DE_EXACT
     if (land_surely_missed(pos + dir * ray_dist, dir, ray_dist, height_scale)) return -1.0f;
+    ray_dist += skip_to_terrain_top(pos + dir * ray_dist, dir, ray_dist, height_scale);
 #endif
     for (int i = 0; i < 250; ++i) {
         float3 ro = pos + dir * ray_dist;
+#if !DE_EXACT
+        if (march_surely_missed(ro, dir, dot(ro, ro), ray_dist, height_scale)) return -1.0f;
+#endif
         float dist = land_sdf<COUNT>(s, ro, height_scale, cn);
         ray_dist += dist;
         if (ray_dist > max_ray_dist || fabsf(dist) < ray_dist * 0.0001f) break;

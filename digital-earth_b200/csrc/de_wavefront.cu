@@ -92,6 +92,7 @@ struct WfParams {
     unsigned int n_chunks;
     int n_spp, x0, y0, w, h, tiles_x;
     uint32_t seed, first_sample;
+    unsigned long long *prof;  // counting build: per stage {cycles, visits, lanes}, + idle cycles at index ST_COUNT
 };
 
 #ifndef WF_PHILOX_UNROLL
@@ -333,7 +334,7 @@ DE_DEV uint32_t setup_sdf(const Ctx &c, int slot, uint32_t pk, float3 o, float3 
         c.pool.t[slot] = -1.0f;
         return PK_SET_STAGE(pk, ST_SDF_DONE);
     }
-    c.pool.t[slot] = ray_dist;
+    c.pool.t[slot] = ray_dist + skip_to_terrain_top(o + d * ray_dist, d, ray_dist, c.s.land_height_scale);
     return PK_SET_STAGE(pk, ST_SDF);
 }
 // top of the scatter loop (pathtracer.py:349-359)
@@ -458,11 +459,12 @@ template <bool COUNT> DE_DEV void burst_sdf(Ctx &c, int slot) {
             float3 ro = o + d * t;
             DE_COUNT(c.cn, C_SDF); DE_COUNT(c.cn, C_TEX);
             float r2 = dot(ro, ro), inv_r = rsqrtf(r2);
+            const bool gone = march_surely_missed(ro, d, r2, t, scale);  // exact: the march would run off to 10 R
             float dist = r2 * inv_r - kPlanetR - scale * sample_sphere_r8_inv(c.s.tex[1], ro, inv_r);
             t += dist;
             ++iter;
-            if (t > 63710000.0f || fabsf(dist) < t * 0.0001f || iter >= 250u) {
-                c.pool.t[slot] = t < 63710000.0f ? t : -1.0f;
+            if (gone || t > 63710000.0f || fabsf(dist) < t * 0.0001f || iter >= 250u) {
+                c.pool.t[slot] = (t < 63710000.0f && !gone) ? t : -1.0f;
                 c.pool.pk[slot] = PK_SET_STAGE(c.pool.pk[slot], ST_SDF_DONE);
                 active = false; pending = true; pend_slot = slot;
             }
@@ -642,11 +644,12 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
         float3 px_ = f3(land_pos.x - eps, land_pos.y, land_pos.z), py_ = f3(land_pos.x, land_pos.y - eps, land_pos.z), pz_ = f3(land_pos.x, land_pos.y, land_pos.z - eps);
         float3 nrm = normalize(f3(sd0 - (length(px_) - kPlanetR - hs * r8_ool(c.s.tex[1], px_)), sd0 - (length(py_) - kPlanetR - hs * r8_ool(c.s.tex[1], py_)),
                                   sd0 - (length(pz_) - kPlanetR - hs * r8_ool(c.s.tex[1], pz_))));
-        LandMaterial m;
-        m.ocean = r8_ool(c.s.tex[2], land_pos);
-        m.albedo_srgb = grade_albedo(rgb8_ool(c.s.tex[0], land_pos), m.ocean);
-        m.bathymetry = r8_ool(c.s.tex[4], land_pos);
-        m.emissive = r8_ool(c.s.tex[5], land_pos);
+        LandMaterial m;  // one equirect mapping for the four material maps
+        const float2 muv = sphere_uv_ool(land_pos.x, land_pos.y, land_pos.z);
+        m.ocean = tex_r8(c.s.tex[2], muv.x, muv.y);
+        m.albedo_srgb = grade_albedo(tex_rgb8(c.s.tex[0], muv.x, muv.y), m.ocean);
+        m.bathymetry = tex_r8(c.s.tex[4], muv.x, muv.y);
+        m.emissive = tex_r8(c.s.tex[5], muv.x, muv.y);
         float albedo = lr.s2s_valid != 0.0f ? dot(m.albedo_srgb, f3(lr.s2s_r, lr.s2s_g, lr.s2s_b)) : 0.0f;
         c.pool.L[slot] += c.pool.thr[slot] * m.emissive * lr.nightlights_power;
         float3 offset_pos = land_pos * (1.0f + 0.0001f * c.s.land_height_scale / 12000.0f);
@@ -747,7 +750,9 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         key = __shfl_sync(full, key, 0);
         if (key == 0) {
             if (wl & 2) break;  // every slot found the work counter exhausted
+            long long t0i = COUNT ? clock64() : 0;
             __nanosleep(64);
+            if (COUNT && lane == 0 && P.prof) atomicAdd(&P.prof[3 * ST_COUNT], (unsigned long long)(clock64() - t0i));
             continue;
         }
         const uint32_t st = (uint32_t)(key & 15);
@@ -756,6 +761,7 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         int slot;
         int n = q_pop(pool, st, 32, lane, slot);
         if (n == 0) continue;
+        const long long t0s = COUNT ? clock64() : 0;
         // 3. run the stage
         if (st == ST_SDF) burst_sdf<COUNT>(c, slot);
 #if WF_TRACK_TEMPLATE
@@ -784,6 +790,11 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
             if (has) c.pool.pk[slot] = npk;
             q_push_sorted(pool, has, PK_STAGE(npk), slot, lane);
         }
+        if (COUNT && lane == 0 && P.prof) {
+            atomicAdd(&P.prof[3 * st], (unsigned long long)(clock64() - t0s));
+            atomicAdd(&P.prof[3 * st + 1], 1ull);
+            atomicAdd(&P.prof[3 * st + 2], (unsigned long long)n);
+        }
     }
     if (COUNT) cn.flush(s.counters);
 }
@@ -793,6 +804,7 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
 struct DeWavefrontState {
     int device = 0, sm_count = 0;
     unsigned int *d_next = nullptr;
+    unsigned long long *d_prof = nullptr;
     bool attr_set = false;
 };
 
@@ -801,11 +813,14 @@ DeWavefrontState *de_wavefront_alloc(int device) {
     st->device = device;
     cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (cudaMalloc(&st->d_next, sizeof(unsigned int)) != cudaSuccess) { delete st; return nullptr; }
+    if (cudaMalloc(&st->d_prof, sizeof(unsigned long long) * 32) != cudaSuccess) { cudaFree(st->d_next); delete st; return nullptr; }
+    cudaMemset(st->d_prof, 0, sizeof(unsigned long long) * 32);
     return st;
 }
 void de_wavefront_free(DeWavefrontState *st) {
     if (!st) return;
     cudaFree(st->d_next);
+    cudaFree(st->d_prof);
     delete st;
 }
 void de_wavefront_render(DeWavefrontState *st, const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0,
@@ -824,7 +839,14 @@ void de_wavefront_render(DeWavefrontState *st, const DevScene &s, float *accum, 
     P.n_chunks = (unsigned)tiles * (unsigned)n_spp * 4u;
     P.n_spp = n_spp; P.x0 = x0; P.y0 = y0; P.w = w; P.h = h; P.seed = seed; P.first_sample = first_sample;
     cudaMemsetAsync(st->d_next, 0, sizeof(unsigned int), stream);
+    P.prof = count ? st->d_prof : nullptr;
+    if (count) cudaMemsetAsync(st->d_prof, 0, sizeof(unsigned long long) * 32, stream);
     int grid = st->sm_count;
     if (count) k_render_wavefront<true><<<grid, WF_WARPS * 32, smem, stream>>>(s, P);
     else k_render_wavefront<false><<<grid, WF_WARPS * 32, smem, stream>>>(s, P);
+}
+
+int de_wavefront_profile(DeWavefrontState *st, unsigned long long *out32) {
+    if (!st) return -1;
+    return cudaMemcpy(out32, st->d_prof, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }

@@ -136,6 +136,16 @@ class Renderer:
         self._check(self._lib.de_get_counters(self._ctx, C.byref(c)))
         return c.as_dict()
 
+    def stage_profile(self):
+        """Scheduler self-profile of the last counting accumulate(): {stage: (warp cycles, visits, slots)} + idle."""
+        import numpy as np
+        buf = np.zeros(32, np.uint64)
+        self._check(self._lib.de_get_stage_profile(self._ctx, buf.ctypes.data_as(C.c_void_p)))
+        names = ("NEW", "SDF", "RMO", "CLOUD", "SDF_DONE", "RMO_DONE", "EVENT", "NEE_DONE")
+        out = {n: tuple(int(x) for x in buf[3 * i:3 * i + 3]) for i, n in enumerate(names)}
+        out["IDLE"] = (int(buf[24]), 0, 0)
+        return out
+
     def _bind_stream(self):
         self._check(self._lib.de_set_stream(self._ctx, C.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)))
 

@@ -125,6 +125,9 @@ int de_fetch_image_host(de_ctx *ctx, float *host_out, int spp_total);
 int de_sync(de_ctx *ctx);
 int de_get_counters(de_ctx *ctx, DeCounters *out); /* synchronises */
 int de_set_counting(de_ctx *ctx, int enabled);     /* counters cost atomics: off by default */
+/* scheduler self-profile of the last counting de_accumulate (wavefront mode): out32[3*s+{0,1,2}] = warp cycles,
+ * visits and slots handled by stage s (NEW, SDF, RMO, CLOUD, SDF_DONE, RMO_DONE, EVENT, NEE_DONE), out32[24] = idle cycles */
+int de_get_stage_profile(de_ctx *ctx, uint64_t *out32);
 
 /* ---- test hooks: the deterministic sub-paths of SURVEY 8(a), DEVICE pointers, n items --------
  * Each evaluates the IEEE source-order (parity) flavour of one reference function. */

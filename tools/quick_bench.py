@@ -46,9 +46,12 @@ for scene in a.scenes.split(","):
             rel = ((acc - ref).abs().mean() / ref.abs().mean()).item()
             line += "  mean|diff|/mean vs first %.4f" % rel
         if a.count:
-            r.set_counting(True); r.reset_framebuffer(); r.accumulate(a.spp); c = r.counters(); r.set_counting(False)
+            r.set_counting(True); r.reset_framebuffer(); r.accumulate(a.spp); c = r.counters(); prof = r.stage_profile() if mode == 'wavefront' else None; r.set_counting(False)
             p = max(c["paths"], 1)
             line += "  per path: seg %.2f rmo %.1f cloud %.1f sdf %.1f tex %.1f surf %.2f" % (
                 c["segments"] / p, c["rmo_steps"] / p, c["cloud_steps"] / p, c["sdf_evals"] / p, c["tex_fetches"] / p, c["surface_hits"] / p)
         print(line, flush=True)
+        if a.count and mode == 'wavefront' and prof:
+            tot = sum(v[0] for v in prof.values())
+            print('    stage share of warp cycles: ' + '  '.join('%s %.1f%% (%.1f slots/visit)' % (k, 100.0 * v[0] / tot, v[2] / max(v[1], 1)) for k, v in prof.items()), flush=True)
     r.close()
