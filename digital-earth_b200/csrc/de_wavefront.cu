@@ -35,6 +35,9 @@ namespace de_fast {
 #ifndef WF_MIN_ACTIVE
 #define WF_MIN_ACTIVE 20  // a burst ends when fewer lanes than this are busy and the queue is dry
 #endif
+#ifndef WF_PHASE
+#define WF_PHASE 32  // SM-wide phase: all warps prefer one stage while it has a full group (I-cache: +11-23 %, profiles/r1_bench.md)
+#endif
 #ifndef WF_STICKY
 #define WF_STICKY 64
 #endif
@@ -83,6 +86,7 @@ struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
     unsigned int q_tail[ST_COUNT], q_head[ST_COUNT];
     int q_avail[ST_COUNT];
     int retired;     // slots that found no more work
+    int phase;       // SM-wide preferred stage (WF_PHASE)
     int work_left;
 };
 
@@ -728,14 +732,15 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         pool.q_head[threadIdx.x] = 0u;
         pool.q_avail[threadIdx.x] = threadIdx.x == ST_NEW ? WF_SLOTS : 0;
     }
-    if (threadIdx.x == 0) { pool.retired = 0; pool.work_left = 1; }
+    if (threadIdx.x == 0) { pool.retired = 0; pool.work_left = 1; pool.phase = 0; }
     __syncthreads();
     int last_st = -1;
     for (;;) {
         // 1. pick the fullest stage queue (free slots only count in whole chunks of 32 while work remains)
         int wl = 0;
-        if (lane == 0) wl = *(volatile int *)&pool.work_left | (*(volatile int *)&pool.retired >= WF_SLOTS ? 2 : 0);
+        if (lane == 0) wl = *(volatile int *)&pool.work_left | (*(volatile int *)&pool.retired >= WF_SLOTS ? 2 : 0) | (*(volatile int *)&pool.phase << 8);
         wl = __shfl_sync(full, wl, 0);  // warp-uniform snapshot
+        const int phase = wl >> 8;
         const bool work_left = (wl & 1) != 0;
         int av = lane < (int)ST_COUNT ? *(volatile int *)&pool.q_avail[lane] : 0;
         if (lane == (int)ST_NEW && work_left && av < 32) av = 0;
@@ -744,6 +749,9 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         int key = av > 0 ? (av << 4) | lane : 0;
 #if WF_STICKY
         if (lane == last_st && av >= WF_STICKY) key += 1 << 20;  // stay on the stage whose code is warm while it has a full group
+#endif
+#if WF_PHASE
+        if (lane == phase && av >= WF_PHASE) key += 1 << 21;     // SM-wide phase: everybody on the same body while it lasts
 #endif
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(full, key, o));
@@ -757,6 +765,9 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         }
         const uint32_t st = (uint32_t)(key & 15);
         last_st = (int)st;
+#if WF_PHASE
+        if ((int)st != phase && lane == 0) pool.phase = (int)st;  // the phase stage ran low: whoever notices moves the SM on
+#endif
         // 2. take up to 32 ready slots
         int slot;
         int n = q_pop(pool, st, 32, lane, slot);
