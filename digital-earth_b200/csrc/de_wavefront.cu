@@ -41,6 +41,9 @@ namespace de_fast {
 #ifndef WF_STICKY
 #define WF_STICKY 64
 #endif
+#ifndef WF_MIN_FRAC8
+#define WF_MIN_FRAC8 5   // ... or this many eighths of the lanes the burst started with
+#endif
 #ifndef WF_REFILL_MIN
 #define WF_REFILL_MIN 6  // idle lanes that trigger a mid-burst refill
 #endif
@@ -100,7 +103,7 @@ struct WfParams {
 };
 
 #ifndef WF_PHILOX_UNROLL
-#define WF_PHILOX_UNROLL 1  // rolled on purpose: 10 unrolled rounds are 2.8 KB of the hottest shared code (I-cache)
+#define WF_PHILOX_UNROLL 5  // partly rolled: 10 unrolled rounds are 2.8 KB of the hottest shared code (I-cache); 5 measured best
 #endif
 constexpr int kPhiloxUnroll = WF_PHILOX_UNROLL;
 // One Philox4x32-10 block; deliberately NOT inlined: ~70 instructions that would otherwise be
@@ -454,7 +457,7 @@ template <bool COUNT> DE_DEV void burst_sdf(Ctx &c, int slot) {
     uint32_t iter = 0u;
     auto load = [&]() { o = ld_o(c, slot); d = ld_d(c, slot); t = c.pool.t[slot]; iter = c.pool.draw[slot] >> 24; };
     if (active) load();
-    const int min_active = min(WF_MIN_ACTIVE, (__popc(__ballot_sync(full, active)) + 1) / 2);
+    const int min_active = min(WF_MIN_ACTIVE, (__popc(__ballot_sync(full, active)) * WF_MIN_FRAC8 + 7) / 8);  // leave the burst when this few lanes are busy
     const float scale = c.s.land_height_scale;
     bool pending = false;
     int pend_slot = -1;
@@ -517,7 +520,7 @@ template <bool COUNT> DE_DEV void burst_track(Ctx &c, int slot, const bool IS_CL
         inv_max = 1.0f / max_ext;
     };
     if (active) load();
-    const int min_active = min(WF_MIN_ACTIVE, (__popc(__ballot_sync(full, active)) + 1) / 2);
+    const int min_active = min(WF_MIN_ACTIVE, (__popc(__ballot_sync(full, active)) * WF_MIN_FRAC8 + 7) / 8);  // leave the burst when this few lanes are busy
     bool pending = false;
     int pend_slot = -1;
     uint32_t pend_st = ST_RMO_DONE;
