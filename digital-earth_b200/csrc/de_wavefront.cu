@@ -102,6 +102,20 @@ struct WfParams {
     unsigned long long *prof;  // counting build: per stage {cycles, visits, lanes}, + idle cycles at index ST_COUNT
 };
 
+#ifndef WF_SPACE_SHORTCUT
+#define WF_SPACE_SHORTCUT 1
+#endif
+#ifndef WF_CHAIN
+#define WF_CHAIN 0   // >0: one-shot stages hand their largest group of successors (>= this many lanes) straight to the next stage, no queue
+                     // round trip.  Measured 8-10 % SLOWER at 8/16/24 (profiles/r1_bench.md): it breaks the SM-wide phase, and the
+                     // instruction cache matters more than the queue traffic.  Kept for the record, off.
+#endif
+#ifndef WF_CHAIN_TOPUP
+#define WF_CHAIN_TOPUP 4  // idle lanes of a chained group that trigger a top-up from the next stage's queue
+#endif
+#ifndef WF_BACKOFF_NS
+#define WF_BACKOFF_NS 0  // sleep after a pop that lost the race for the last group of a queue (idle warps otherwise spin through the scheduler)
+#endif
 #ifndef WF_PHILOX_UNROLL
 #define WF_PHILOX_UNROLL 5  // partly rolled: 10 unrolled rounds are 2.8 KB of the hottest shared code (I-cache); 5 measured best
 #endif
@@ -378,6 +392,7 @@ DE_DEV uint32_t stage_rmo_done(Ctx &c, int slot) {
 // exactly 32 free slots, one per lane; claims one work chunk = 32 neighbouring pixels, one sample.
 // Returns the new pk (ST_SDF), ST_NEW to hand the slot back (pixel outside the window), or ~0u
 // when no work is left.
+template <bool COUNT> DE_DEV uint32_t end_path(Ctx &c, int slot, uint32_t pk, bool primary_miss, float3 dir);
 template <bool COUNT> DE_DEV uint32_t stage_new(Ctx &c, int slot) {
     const unsigned full = 0xFFFFFFFFu;
     const WfParams &P = c.P;
@@ -398,8 +413,14 @@ template <bool COUNT> DE_DEV uint32_t stage_new(Ctx &c, int slot) {
     float3 dir = get_cast_dir(c.s, c.dv, (float)px, (float)py, xu, xv);
     c.pool.pix[slot] = rng.key1; c.pool.sample[slot] = rng.sample;
     c.pool.thr[slot] = 1.0f; c.pool.L[slot] = 0.0f;
-    st_o(c, slot, c.s.cam_pos); st_d(c, slot, dir);
     DE_COUNT(c.cn, C_SEGMENTS);
+#if WF_SPACE_SHORTCUT
+    // A primary ray that misses the atmosphere shell interacts with nothing (every later test of the
+    // segment uses a smaller sphere): it is a primary miss right here (pathtracer.py:441-444,455-466),
+    // instead of five queue hops.  rsi keeps the reference's NaN-on-miss behaviour, hence the negation.
+    if (!(rsi(c.s.cam_pos, dir, kAtmosUpper).y >= 0.0f)) return end_path<COUNT>(c, slot, PK_SET_LAM(0u, (uint32_t)bin), true, dir);
+#endif
+    st_o(c, slot, c.s.cam_pos); st_d(c, slot, dir);
     return begin_segment(c, slot, PK_SET_LAM(0u, (uint32_t)bin), c.s.cam_pos, dir);
 }
 // pathtracer.py:455-469 + renderer.py:329-330; frees the slot
@@ -738,44 +759,55 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
     if (threadIdx.x == 0) { pool.retired = 0; pool.work_left = 1; pool.phase = 0; }
     __syncthreads();
     int last_st = -1;
+    bool chained = false;  // the warp already holds slots of stage `st` (handed over by the previous one-shot stage)
+    uint32_t st = 0u;
+    int slot = -1, n = 0;
+    bool work_left = true;
     for (;;) {
-        // 1. pick the fullest stage queue (free slots only count in whole chunks of 32 while work remains)
-        int wl = 0;
-        if (lane == 0) wl = *(volatile int *)&pool.work_left | (*(volatile int *)&pool.retired >= WF_SLOTS ? 2 : 0) | (*(volatile int *)&pool.phase << 8);
-        wl = __shfl_sync(full, wl, 0);  // warp-uniform snapshot
-        const int phase = wl >> 8;
-        const bool work_left = (wl & 1) != 0;
-        int av = lane < (int)ST_COUNT ? *(volatile int *)&pool.q_avail[lane] : 0;
-        if (lane == (int)ST_NEW && work_left && av < 32) av = 0;
-        // plain fullest-queue policy: stage affinity per sub-partition and role-specialised warps were
-        // both measured slower (profiles/r1_wavefront.md, "scheduling experiments")
-        int key = av > 0 ? (av << 4) | lane : 0;
+        if (!chained) {
+            // 1. pick the fullest stage queue (free slots only count in whole chunks of 32 while work remains)
+            int wl = 0;
+            if (lane == 0) wl = *(volatile int *)&pool.work_left | (*(volatile int *)&pool.retired >= WF_SLOTS ? 2 : 0) | (*(volatile int *)&pool.phase << 8);
+            wl = __shfl_sync(full, wl, 0);  // warp-uniform snapshot
+            const int phase = wl >> 8;
+            work_left = (wl & 1) != 0;
+            int av = lane < (int)ST_COUNT ? *(volatile int *)&pool.q_avail[lane] : 0;
+            if (lane == (int)ST_NEW && work_left && av < 32) av = 0;
+            // plain fullest-queue policy: stage affinity per sub-partition and role-specialised warps were
+            // both measured slower (profiles/r1_wavefront.md, "scheduling experiments")
+            int key = av > 0 ? (av << 4) | lane : 0;
 #if WF_STICKY
-        if (lane == last_st && av >= WF_STICKY) key += 1 << 20;  // stay on the stage whose code is warm while it has a full group
+            if (lane == last_st && av >= WF_STICKY) key += 1 << 20;  // stay on the stage whose code is warm while it has a full group
 #endif
 #if WF_PHASE
-        if (lane == phase && av >= WF_PHASE) key += 1 << 21;     // SM-wide phase: everybody on the same body while it lasts
+            if (lane == phase && av >= WF_PHASE) key += 1 << 21;     // SM-wide phase: everybody on the same body while it lasts
 #endif
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(full, key, o));
-        key = __shfl_sync(full, key, 0);
-        if (key == 0) {
-            if (wl & 2) break;  // every slot found the work counter exhausted
-            long long t0i = COUNT ? clock64() : 0;
-            __nanosleep(64);
-            if (COUNT && lane == 0 && P.prof) atomicAdd(&P.prof[3 * ST_COUNT], (unsigned long long)(clock64() - t0i));
-            continue;
+            key = __reduce_max_sync(full, key);
+            if (key == 0) {
+                if (wl & 2) break;  // every slot found the work counter exhausted
+                long long t0i = COUNT ? clock64() : 0;
+                __nanosleep(WF_BACKOFF_NS > 64 ? WF_BACKOFF_NS : 64);
+                if (COUNT && lane == 0 && P.prof) atomicAdd(&P.prof[3 * ST_COUNT], (unsigned long long)(clock64() - t0i));
+                continue;
+            }
+            st = (uint32_t)(key & 15);
+            last_st = (int)st;
+#if WF_PHASE
+            if ((int)st != phase && lane == 0) pool.phase = (int)st;  // the phase stage ran low: whoever notices moves the SM on
+#endif
+            // 2. take up to 32 ready slots
+            n = q_pop(pool, st, 32, lane, slot);
+            if (n == 0) {
+#if WF_BACKOFF_NS
+                __nanosleep(WF_BACKOFF_NS);
+#endif
+                continue;
+            }
         }
-        const uint32_t st = (uint32_t)(key & 15);
-        last_st = (int)st;
-#if WF_PHASE
-        if ((int)st != phase && lane == 0) pool.phase = (int)st;  // the phase stage ran low: whoever notices moves the SM on
-#endif
-        // 2. take up to 32 ready slots
-        int slot;
-        int n = q_pop(pool, st, 32, lane, slot);
-        if (n == 0) continue;
+        chained = false;
         const long long t0s = COUNT ? clock64() : 0;
+        const uint32_t st_run = st;
+        const int n_run = n;
         // 3. run the stage
         if (st == ST_SDF) burst_sdf<COUNT>(c, slot);
 #if WF_TRACK_TEMPLATE
@@ -802,12 +834,41 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
                 else npk = stage_nee_done<COUNT>(c, slot);
             }
             if (has) c.pool.pk[slot] = npk;
-            q_push_sorted(pool, has, PK_STAGE(npk), slot, lane);
+            const uint32_t tgt = PK_STAGE(npk);
+#if WF_CHAIN
+            // hand the largest group of successors straight to its stage: no queue round trip for them
+            const unsigned grp = __match_any_sync(full, has ? tgt : 15u);
+            const unsigned best = __reduce_max_sync(full, has ? ((unsigned)__popc(grp) << 4) | tgt : 0u);
+            const uint32_t cst = best & 15u;
+            const int cn_ = (int)(best >> 4);
+            if (cn_ >= WF_CHAIN && (cst != ST_NEW || cn_ == 32)) {
+                const bool keep = has && tgt == cst;
+                q_push_sorted(pool, has && !keep, tgt, slot, lane);
+                if (!keep) slot = -1;
+                n = cn_;
+                if (32 - cn_ >= WF_CHAIN_TOPUP && cst != ST_NEW) {  // fill the idle lanes from the successor's queue
+                    int av2 = 0;
+                    if (lane == 0) av2 = *(volatile int *)&pool.q_avail[cst];
+                    if (__shfl_sync(full, av2, 0) > 0) {
+                        int got;
+                        const int m = q_pop(pool, cst, 32 - cn_, lane, got);
+                        const unsigned km = __ballot_sync(full, keep);
+                        const int rank = __popc(~km & ((1u << lane) - 1u));
+                        const int mine = __shfl_sync(full, got, rank & 31);
+                        if (!keep && rank < m) slot = mine;
+                        n += m;
+                    }
+                }
+                st = cst;
+                chained = true;
+            } else
+#endif
+            q_push_sorted(pool, has, tgt, slot, lane);
         }
         if (COUNT && lane == 0 && P.prof) {
-            atomicAdd(&P.prof[3 * st], (unsigned long long)(clock64() - t0s));
-            atomicAdd(&P.prof[3 * st + 1], 1ull);
-            atomicAdd(&P.prof[3 * st + 2], (unsigned long long)n);
+            atomicAdd(&P.prof[3 * st_run], (unsigned long long)(clock64() - t0s));
+            atomicAdd(&P.prof[3 * st_run + 1], 1ull);
+            atomicAdd(&P.prof[3 * st_run + 2], (unsigned long long)n_run);
         }
     }
     if (COUNT) cn.flush(s.counters);

@@ -1,0 +1,6 @@
+cd $GRAFT_REPO_ROOT
+for v in _s1 _bo128 _bo512 _bo2000 _w24 _w24bo512 _w28bo512; do
+  echo "=== variant libde$v"
+  DE_LIB_PATH=$PWD/digital-earth_b200/libde$v.so timeout 300 python tools/quick_bench.py --res 1920x1080 --spp 16 --modes wavefront 2>&1 | grep -v "^scene"
+done > gpurun_out/sweep2.log 2>&1
+tail -40 gpurun_out/sweep2.log

@@ -8,7 +8,8 @@ import sys
 
 rep, cubin, kernel_tag = sys.argv[1], sys.argv[2], sys.argv[3]
 src_file = sys.argv[4] if len(sys.argv) > 4 else 'de_wavefront.cu'
-sass = subprocess.run(['nvdisasm', '-g', '-c', cubin], capture_output=True, text=True).stdout
+INNER = len(sys.argv) > 6 and sys.argv[6] == 'inner'
+sass = subprocess.run(['nvdisasm', '-gi', '-c', cubin], capture_output=True, text=True).stdout
 addr2loc, chain, infn, marker_run = {}, [], False, False
 for ln in sass.splitlines():
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
@@ -44,7 +45,7 @@ for r in rows[2:]:
     key = ('?', 0)
     if loc:
         wf = [l for l in loc if l[0] == src_file]
-        key = wf[-1] if wf else loc[-1]   # outermost line in the kernel's own file
+        key = (wf[0] if INNER else wf[-1]) if wf else loc[-1]   # innermost / outermost line in the kernel's own file
     for t, v in zip((0, 1, 2), (inst, thr, smp)):
         agg[key][t] += v
         tot[t] += v
