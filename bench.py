@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--cpu-res", default="480x272")
     ap.add_argument("--cpu-spp", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "fused"],
+                    help="N>1: ncclReduce of the accumulation buffers, or rank 0's resolve kernel reading the peers' buffers over NVLink P2P")
     return ap.parse_args()
 
 
@@ -185,6 +187,13 @@ def main():
     r.copy_textures()
     host_img = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    fused = a.exchange == "fused" and world > 1
+    peers, token = [], torch.zeros(1, device=dev)
+    if fused:  # map the other ranks' accumulation buffers once (CUDA IPC over NVLink peer memory)
+        handles = [None] * world
+        dist.all_gather_object(handles, r.export_accum_handle())
+        if rank == 0:
+            peers = [r.open_peer(handles[k]) for k in range(1, world)]
 
     def step(e2e):
         flush.fill_(1)  # evict L2 between timed iterations (textures alone are 416 MB > L2 as well)
@@ -192,9 +201,16 @@ def main():
             r.apply_config(cfg)   # host -> device: scene parameters for this frame
         r.reset_framebuffer()
         r.accumulate(spp_local, first_sample=first)
-        reduce_accumulation(r.color_buffer, dst=0)  # ncclReduce(sum) over NVLink: the path's one exchange step (no-op at N=1)
+        if fused:
+            # exchange fused into the resolve: a 4-byte all-reduce is the stream-ordered "all ranks have rendered" barrier,
+            # rank 0's resolve kernel then sums the peers' buffers in place, a second token releases the buffers
+            dist.all_reduce(token)
+            img = r.fetch_image_peers(peers, a.spp) if rank == 0 else None
+            dist.all_reduce(token)
+        else:
+            reduce_accumulation(r.color_buffer, dst=0)  # ncclReduce(sum) over NVLink: the path's one exchange step (no-op at N=1)
+            img = r.fetch_image(spp=a.spp) if e2e and rank == 0 else None
         if e2e and rank == 0:
-            img = r.fetch_image(spp=a.spp)
             host_img.copy_(img.permute(1, 0, 2), non_blocking=True)  # device -> pinned host ([H][W][3] storage order)
 
     def timed(e2e, n):
@@ -261,10 +277,11 @@ def main():
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s (config - %s.txt), %dx%d, %d spp, synthetic %dx%d textures" % (a.scene, SCENES[a.scene], W, H, a.spp, tw, th),
                        "scene": a.scene, "integrator": a.mode, "ms_per_frame": ms / a.steps, "ms_per_spp": ms / a.steps / a.spp,
-                       "partition": "spp-slice x%d + ncclReduce(sum) of the f32 accumulation buffer" % world if world > 1 else "single GPU",
+                       "partition": ("spp-slice x%d + %s" % (world, "resolve kernel summing the peers' f32 accumulation buffers over NVLink P2P (CUDA IPC)" if fused
+                                                             else "ncclReduce(sum) of the f32 accumulation buffer")) if world > 1 else "single GPU",
                        "l2": "256 MiB flush between steps; textures (416 MB) exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": 96, "d2h_bytes_per_step": W * H * 3 * 4},
-            "gpu_launches": a.steps * 1,  # one k_render_wavefront launch per step (memsets and the NCCL reduce are not ours)
+            "gpu_launches": a.steps * (2 if fused else 1),  # k_render_wavefront (+ k_resolve_peers with --exchange fused) per step; memsets and NCCL are not ours
             "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                          "traffic": traffic, "kernel": "k_render_wavefront", "kernel_ms": kernel_ms, "flop_per_path": fpp,
                          "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (max SM clock of MEASURED_PEAKS.json); HBM/tensor peaks do not bound this path" % sm_max,
@@ -277,6 +294,12 @@ def main():
             paths, times, sample, cores, _ = cpu_baseline(a, steps=1, textures=tex)
             line["cpu_baseline"] = {"value": paths / times[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
+    if fused:
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            r.close_peers()
+        dist.barrier()
     r.close()
     if world > 1:
         dist.destroy_process_group()

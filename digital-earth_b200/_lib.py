@@ -48,6 +48,10 @@ _SIGS = {
     "de_accumulate": ([_P, _I, _U, _U, _I, _I, _I, _I], _I),
     "de_get_accum": ([_P, C.POINTER(_P)], _I),
     "de_resolve": ([_P, _P, _P, _I], _I),
+    "de_ipc_export_accum": ([_P, _P], _I),
+    "de_ipc_open_peer": ([_P, _P, C.POINTER(_P)], _I),
+    "de_ipc_close_peers": ([_P], _I),
+    "de_resolve_peers": ([_P, C.POINTER(_P), _I, _P, _I], _I),
     "de_fetch_image_host": ([_P, _P, _I], _I),
     "de_sync": ([_P], _I),
     "de_get_counters": ([_P, C.POINTER(DeCounters)], _I),

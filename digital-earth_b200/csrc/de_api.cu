@@ -29,6 +29,7 @@ struct de_ctx {
     uint8_t *d_cloud_max = nullptr;
     unsigned long long *d_counters = nullptr;
     DeWavefrontState *wf = nullptr;
+    std::vector<void *> ipc_open;  // peer buffers opened with de_ipc_open_peer
     std::string err;
 };
 
@@ -125,6 +126,7 @@ void de_destroy(de_ctx *ctx) {
         cudaFree(ctx->d_tex[i]);
     }
     de_wavefront_free(ctx->wf);
+    for (void *p : ctx->ipc_open) cudaIpcCloseMemHandle(p);
     cudaFree(ctx->d_cie); cudaFree(ctx->d_s2s); cudaFree(ctx->d_o3); cudaFree(ctx->d_crf); cudaFree(ctx->d_cdf);
     cudaFree(ctx->d_cloud_max);
     cudaFree(ctx->d_lam); cudaFree(ctx->d_derived); cudaFree(ctx->d_accum); cudaFree(ctx->d_image); cudaFree(ctx->d_counters);
@@ -284,6 +286,55 @@ int de_resolve(de_ctx *ctx, const float *accum_override, float *dev_out, int spp
     if (ctx->mode == DE_MODE_PARITY) de_exact::launch_resolve(ctx->scene, src, dev_out, spp_total, ctx->stream);
     else de_fast::launch_resolve(ctx->scene, src, dev_out, spp_total, ctx->stream);
     return check_launch(ctx, "resolve");
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI documents a 64-byte handle");
+int de_ipc_export_accum(de_ctx *ctx, void *handle64) {
+    ENTER();
+    NEED(handle64, "handle64 is NULL");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->d_accum));
+    std::memcpy(handle64, &h, sizeof(h));
+    return DE_OK;
+}
+
+int de_ipc_open_peer(de_ctx *ctx, const void *handle64, float **dev_ptr) {
+    ENTER();
+    NEED(handle64 && dev_ptr, "handle64 / dev_ptr is NULL");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    void *p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->ipc_open.push_back(p);
+    *dev_ptr = static_cast<float *>(p);
+    return DE_OK;
+}
+
+int de_ipc_close_peers(de_ctx *ctx) {
+    ENTER();
+    CU(cudaStreamSynchronize(ctx->stream));  // a resolve may still be reading them
+    int rc = DE_OK;
+    for (void *p : ctx->ipc_open) {
+        cudaError_t e = cudaIpcCloseMemHandle(p);
+        if (e != cudaSuccess) rc = fail(ctx, DE_ERR_CUDA, std::string("cudaIpcCloseMemHandle: ") + cudaGetErrorString(e));
+    }
+    ctx->ipc_open.clear();
+    return rc;
+}
+
+int de_resolve_peers(de_ctx *ctx, const float *const *peer_accums, int n_peers, float *dev_out, int spp_total) {
+    ENTER();
+    NEED(dev_out, "dev_out is NULL");
+    NEED(spp_total > 0, "spp_total <= 0");
+    NEED(n_peers >= 0 && n_peers <= kDeMaxPeers, "n_peers out of range (0..15)");
+    NEED(n_peers == 0 || peer_accums, "peer_accums is NULL");
+    for (int k = 0; k < n_peers; ++k) NEED(peer_accums[k], "a peer pointer is NULL");
+    if (!ctx->have_params || !ctx->have_luts) return fail(ctx, DE_ERR_STATE, "params / LUTs missing");
+    int rc = refresh_scene(ctx);
+    if (rc) return rc;
+    if (ctx->mode == DE_MODE_PARITY) de_exact::launch_resolve_peers(ctx->scene, ctx->d_accum, peer_accums, n_peers, dev_out, spp_total, ctx->stream);
+    else de_fast::launch_resolve_peers(ctx->scene, ctx->d_accum, peer_accums, n_peers, dev_out, spp_total, ctx->stream);
+    return check_launch(ctx, "resolve_peers");
 }
 
 int de_fetch_image_host(de_ctx *ctx, float *host_out, int spp_total) {

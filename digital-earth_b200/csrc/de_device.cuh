@@ -183,7 +183,11 @@ DE_DEV float3 tex_rgb8_gather(const DevTex &t, float u, float v) {
 #endif
 DE_DEV float tex_r8(const DevTex &t, float u, float v) {
 #if !DE_EXACT
+#if DE_TEX_OBJ_ONLY  // the wavefront kernel: every uploaded map has its texture object (de_upload_texture fails otherwise)
+    return tex_r8_gather(t, u, v);
+#else
     if (t.obj) return tex_r8_gather(t, u, v);
+#endif
 #endif
     Bilin b = bilin_setup(t.w, t.h, u, v);
     const uint8_t *r0 = t.data + (size_t)b.y0 * t.w, *r1 = t.data + (size_t)b.y1 * t.w;
@@ -191,7 +195,11 @@ DE_DEV float tex_r8(const DevTex &t, float u, float v) {
 }
 DE_DEV float3 tex_rgb8(const DevTex &t, float u, float v) {
 #if !DE_EXACT
+#if DE_TEX_OBJ_ONLY
+    return tex_rgb8_gather(t, u, v);
+#else
     if (t.obj) return tex_rgb8_gather(t, u, v);
+#endif
 #endif
     Bilin b = bilin_setup(t.w, t.h, u, v);
     const uint8_t *p00 = t.data + ((size_t)b.y0 * t.w + b.x0) * 3, *p10 = t.data + ((size_t)b.y0 * t.w + b.x1) * 3;

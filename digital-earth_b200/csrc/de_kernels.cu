@@ -51,6 +51,31 @@ void launch_resolve(const DevScene &s, const float *accum, float *out, int spp, 
     int n = s.W * s.H;
     k_resolve<<<(n + 255) / 256, 256, 0, st>>>(s, accum, out, spp);
 }
+// Multi-GPU resolve fused with the accumulation exchange: the partial sums of the other ranks are read
+// straight from their memory (NVLink P2P / same-device pointers) while this pixel is resolved -- no reduce pass, no
+// staging buffer.  Summation order is fixed (own, then peers in rank order), so the image is deterministic.
+struct PeerAccums { const float *p[kDeMaxPeers]; int n; };
+__global__ void __launch_bounds__(256) k_resolve_peers(DevScene s, const float *__restrict__ accum, PeerAccums peers, float *__restrict__ out, int spp) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.W * s.H) return;
+    int i = idx % s.W, j = idx / s.W;
+    OpenDrtPar op = opendrt_params();
+    AgxPar ap;
+    if (s.tonemapper == 1) ap = agx_params();
+    float3 sum = LD3(accum, (size_t)idx);
+    for (int k = 0; k < peers.n; ++k) {
+        const float *q = peers.p[k] + (size_t)idx * 3;
+        sum.x += __ldcv(q); sum.y += __ldcv(q + 1); sum.z += __ldcv(q + 2);  // volatile-class loads: peer memory is not cached across launches
+    }
+    ST3(out, (size_t)idx, resolve_pixel(s, op, ap, i, j, sum, spp));
+}
+void launch_resolve_peers(const DevScene &s, const float *accum, const float *const *peers, int n_peers, float *out, int spp, cudaStream_t st) {
+    PeerAccums pa;
+    pa.n = n_peers;
+    for (int k = 0; k < kDeMaxPeers; ++k) pa.p[k] = k < n_peers ? peers[k] : nullptr;
+    int n = s.W * s.H;
+    k_resolve_peers<<<(n + 255) / 256, 256, 0, st>>>(s, accum, pa, out, spp);
+}
 
 #if !DE_EXACT
 // coarse max-map of the cloud texture: cell (cx,cy) = max over its cm_b x cm_b texels dilated by one

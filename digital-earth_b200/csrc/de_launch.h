@@ -3,11 +3,14 @@
 #include "de_scene.h"
 
 struct DeWavefrontState;  // de_wavefront.cuh
+constexpr int kDeMaxPeers = 15;  // other ranks whose accumulation buffers one resolve can sum (16-GPU node)
 
 #define DE_DECLARE_COMMON                                                                                                              \
     void launch_render_mega(const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w,  \
                             int h, bool count, cudaStream_t st);                                                                       \
-    void launch_resolve(const DevScene &s, const float *accum, float *out, int spp, cudaStream_t st);
+    void launch_resolve(const DevScene &s, const float *accum, float *out, int spp, cudaStream_t st);                                 \
+    void launch_resolve_peers(const DevScene &s, const float *accum, const float *const *peers, int n_peers, float *out, int spp,     \
+                              cudaStream_t st);
 
 namespace de_fast {
 DE_DECLARE_COMMON

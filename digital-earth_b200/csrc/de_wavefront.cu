@@ -17,6 +17,7 @@
 //     work counter (path regeneration): 32 neighbouring pixels of one 16x8 film tile, one sample.
 // The random stream of a path is the contract of include/de_api.h (Philox key (seed,pixel), counter
 // (sample,bounce,slot>>2)), so a pixel's samples are the same paths in every integrator flavour.
+#define DE_TEX_OBJ_ONLY 1
 #include "de_integrator.cuh"
 #include "de_launch.h"
 #include "de_wavefront.h"
@@ -33,7 +34,7 @@ namespace de_fast {
 #define WF_BURST 64    // max loop iterations per burst
 #endif
 #ifndef WF_MIN_ACTIVE
-#define WF_MIN_ACTIVE 20  // a burst ends when fewer lanes than this are busy and the queue is dry
+#define WF_MIN_ACTIVE 24  // a burst ends when fewer lanes than this are busy and the queue is dry
 #endif
 #ifndef WF_PHASE
 #define WF_PHASE 32  // SM-wide phase: all warps prefer one stage while it has a full group (I-cache: +11-23 %, profiles/r1_bench.md)
@@ -42,10 +43,10 @@ namespace de_fast {
 #define WF_STICKY 64
 #endif
 #ifndef WF_MIN_FRAC8
-#define WF_MIN_FRAC8 5   // ... or this many eighths of the lanes the burst started with
+#define WF_MIN_FRAC8 6   // ... or this many eighths of the lanes the burst started with
 #endif
 #ifndef WF_REFILL_MIN
-#define WF_REFILL_MIN 6  // idle lanes that trigger a mid-burst refill
+#define WF_REFILL_MIN 10 // idle lanes that trigger a mid-burst refill
 #endif
 constexpr int WF_RING = 2048;  // ring capacity per stage queue (power of two >= WF_SLOTS)
 static_assert(WF_RING >= WF_SLOTS && (WF_RING & (WF_RING - 1)) == 0 && WF_SLOTS < 2048, "ring / slot-id encoding");
@@ -113,6 +114,12 @@ struct WfParams {
 #ifndef WF_CHAIN_TOPUP
 #define WF_CHAIN_TOPUP 4  // idle lanes of a chained group that trigger a top-up from the next stage's queue
 #endif
+#ifndef WF_OOL_MASK
+#define WF_OOL_MASK 0  // bit 0: end_path out of line, bit 1: setup_sdf out of line
+#endif
+#ifndef WF_TRACK_PHILOX_INLINE
+#define WF_TRACK_PHILOX_INLINE 0
+#endif
 #ifndef WF_BACKOFF_NS
 #define WF_BACKOFF_NS 0  // sleep after a pop that lost the race for the last group of a queue (idle warps otherwise spin through the scheduler)
 #endif
@@ -122,6 +129,17 @@ struct WfParams {
 constexpr int kPhiloxUnroll = WF_PHILOX_UNROLL;
 // One Philox4x32-10 block; deliberately NOT inlined: ~70 instructions that would otherwise be
 // replicated at every draw site and blow the instruction cache (profiles/r1_wavefront.md).
+DE_DEV uint4 philox_block_inl(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2) {
+    uint32_t c3 = 0u;
+#pragma unroll kPhiloxUnroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
 __device__ __noinline__ uint4 philox_block(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2) {
     uint32_t c3 = 0u;
 #pragma unroll kPhiloxUnroll
@@ -156,12 +174,12 @@ struct RngW {
 
 // Out-of-line equirect fetches for the one-shot stages (normals, materials, stars); the loop
 // stages keep their single fetch inline.
-__device__ __noinline__ float fetch_r8_ool(const uint8_t *data, int w, int h, float px, float py, float pz) {
-    DevTex t; t.data = data; t.w = w; t.h = h; t.c = 1; t.obj = 0;
+__device__ __noinline__ float fetch_r8_ool(cudaTextureObject_t obj, int w, int h, float px, float py, float pz) {
+    DevTex t; t.data = nullptr; t.w = w; t.h = h; t.c = 1; t.obj = obj;
     return sample_sphere_r8(t, f3(px, py, pz));
 }
-__device__ __noinline__ float3 fetch_rgb8_ool(const uint8_t *data, int w, int h, float px, float py, float pz) {
-    DevTex t; t.data = data; t.w = w; t.h = h; t.c = 3; t.obj = 0;
+__device__ __noinline__ float3 fetch_rgb8_ool(cudaTextureObject_t obj, int w, int h, float px, float py, float pz) {
+    DevTex t; t.data = nullptr; t.w = w; t.h = h; t.c = 3; t.obj = obj;
     return sample_sphere_rgb8(t, f3(px, py, pz));
 }
 // cold, large bodies shared by the one-shot stages (kept out of line for the instruction cache)
@@ -187,8 +205,8 @@ __device__ __noinline__ float4 phase_sample_ool(float dx, float dy, float dz, in
     return make_float4(d.x, d.y, d.z, pdp);
 }
 __device__ __noinline__ float2 sphere_uv_ool(float px, float py, float pz) { return sphere_uv(f3(px, py, pz)); }
-DE_DEV float r8_ool(const DevTex &t, float3 p) { return fetch_r8_ool(t.data, t.w, t.h, p.x, p.y, p.z); }
-DE_DEV float3 rgb8_ool(const DevTex &t, float3 p) { return fetch_rgb8_ool(t.data, t.w, t.h, p.x, p.y, p.z); }
+DE_DEV float r8_ool(const DevTex &t, float3 p) { return fetch_r8_ool(t.obj, t.w, t.h, p.x, p.y, p.z); }
+DE_DEV float3 rgb8_ool(const DevTex &t, float3 p) { return fetch_rgb8_ool(t.obj, t.w, t.h, p.x, p.y, p.z); }
 
 struct Ctx {  // per-warp context
     const DevScene &s;
@@ -287,40 +305,12 @@ DE_DEV void st_d(const Ctx &c, int s, float3 v) { c.pool.dx[s] = v.x; c.pool.dy[
 DE_DEV float cloud_ext_of(uint32_t sc) { return sc > 9u ? 0.02f : kCloudsExtinct; }  // pathtracer.py:351-352
 
 // ------------------------------------------------------------------ transitions (run converged inside one-shot stages)
-// ratio tracking through the cloud shell (second half of sample_transmittance, pathtracer.py:229-231)
-DE_DEV uint32_t setup_cloud_ratio(const Ctx &c, int slot, uint32_t pk, float3 o, float3 d) {
-    float ts, tm;
-    intersect_cloud_limits(o, d, c.pool.isect[slot], ts, tm);
-    if (ts < tm) {
-        float bound = cloud_density_bound(cloud_segment_cmax(c.s, o, d, ts, tm));
-        if (bound > 0.0f) {
-            c.pool.t[slot] = ts; c.pool.tmax[slot] = tm; c.pool.cmj[slot] = bound;
-            return PK_SET_STAGE(pk, ST_CLOUD) | PK_RATIO;
-        }
-    }
-    return PK_SET_STAGE(pk, ST_NEE_DONE);
-}
 // outcome of sample_interaction (pathtracer.py:200-207) -> EVENT stage
 DE_DEV uint32_t finish_interaction(const Ctx &c, int slot, uint32_t pk, uint32_t ev, float t, uint32_t id) {
     c.pool.t[slot] = t;
     pk = PK_SET_EV(pk, ev);
     pk = PK_SET_ID(pk, id);
     return PK_SET_STAGE(pk, ST_EVENT) & ~PK_RATIO;
-}
-// cloud half of sample_interaction (pathtracer.py:189-198); rmo result is in pk / aux
-DE_DEV uint32_t setup_cloud_delta(const Ctx &c, int slot, uint32_t pk, float3 o, float3 d) {
-    float ts, tm;
-    intersect_cloud_limits(o, d, c.pool.isect[slot], ts, tm);
-    uint32_t rmo_ev = PK_RMO_EV(pk);
-    float rmo_t = c.pool.aux[slot];
-    if ((rmo_ev == kNullEvent || rmo_t > ts) && ts < tm) {
-        float bound = cloud_density_bound(cloud_segment_cmax(c.s, o, d, ts, tm));
-        if (bound > 0.0f) {
-            c.pool.t[slot] = ts; c.pool.tmax[slot] = tm; c.pool.cmj[slot] = bound;
-            return PK_SET_STAGE(pk, ST_CLOUD) & ~PK_RATIO;
-        }
-    }
-    return finish_interaction(c, slot, pk, rmo_ev, rmo_t, PK_RMO_ID(pk));
 }
 // rmo half of sample_interaction / sample_transmittance (pathtracer.py:180-186, 219-227);
 // isect[slot] holds the land intersection that bounds the ray
@@ -346,7 +336,12 @@ DE_DEV uint32_t setup_rmo(const Ctx &c, int slot, uint32_t pk, float3 o, float3 
     return PK_SET_STAGE(pk, ST_RMO_DONE);
 }
 // intersect_land prologue (pathtracer.py:29-35)
-DE_DEV uint32_t setup_sdf(const Ctx &c, int slot, uint32_t pk, float3 o, float3 d, uint32_t draw) {
+#if WF_OOL_MASK & 2
+__device__ __noinline__
+#else
+DE_DEV
+#endif
+uint32_t setup_sdf(const Ctx &c, int slot, uint32_t pk, float3 o, float3 d, uint32_t draw) {
     float ray_dist = 0.0f;
     float2 rd = rsi(o, d, kAtmosUpper);
     if (rd.x > 0.0f) ray_dist = rd.x;
@@ -380,11 +375,29 @@ DE_DEV uint32_t stage_sdf_done(Ctx &c, int slot) {
     c.pool.isect[slot] = isect;
     return setup_rmo(c, slot, pk, o, d, shadow);
 }
-// ST_RMO_DONE: between the rmo pass and the cloud pass of either tracker
+// ST_RMO_DONE: between the rmo pass and the cloud pass of either tracker.  Delta tracking
+// (sample_interaction, pathtracer.py:189-207) enters the shell only if the rmo pass found no collision
+// before it; ratio tracking (sample_transmittance, :229-231) always does.  One copy of the cloud-bound
+// code serves both (instruction cache).
 DE_DEV uint32_t stage_rmo_done(Ctx &c, int slot) {
     uint32_t pk = c.pool.pk[slot];
     float3 o = ld_o(c, slot), d = ld_d(c, slot);
-    return (pk & PK_RATIO) ? setup_cloud_ratio(c, slot, pk, o, d) : setup_cloud_delta(c, slot, pk, o, d);
+    const bool ratio = (pk & PK_RATIO) != 0u;
+    float ts, tm;
+    intersect_cloud_limits(o, d, c.pool.isect[slot], ts, tm);
+    const uint32_t rmo_ev = PK_RMO_EV(pk);
+    const float rmo_t = c.pool.aux[slot];  // delta: distance of the rmo collision; ratio: transmittance so far
+    bool enter = ts < tm;
+    if (!ratio) enter = enter && (rmo_ev == kNullEvent || rmo_t > ts);
+    if (enter) {
+        float bound = cloud_density_bound(cloud_segment_cmax(c.s, o, d, ts, tm));
+        if (bound > 0.0f) {
+            c.pool.t[slot] = ts; c.pool.tmax[slot] = tm; c.pool.cmj[slot] = bound;
+            return PK_SET_STAGE(pk, ST_CLOUD);  // PK_RATIO stays as it is
+        }
+    }
+    if (ratio) return PK_SET_STAGE(pk, ST_NEE_DONE);
+    return finish_interaction(c, slot, pk, rmo_ev, rmo_t, PK_RMO_ID(pk));
 }
 
 // ------------------------------------------------------------------ path start / end
@@ -392,7 +405,12 @@ DE_DEV uint32_t stage_rmo_done(Ctx &c, int slot) {
 // exactly 32 free slots, one per lane; claims one work chunk = 32 neighbouring pixels, one sample.
 // Returns the new pk (ST_SDF), ST_NEW to hand the slot back (pixel outside the window), or ~0u
 // when no work is left.
-template <bool COUNT> DE_DEV uint32_t end_path(Ctx &c, int slot, uint32_t pk, bool primary_miss, float3 dir);
+#if WF_OOL_MASK & 1
+#define WF_ENDPATH_ATTR __device__ __noinline__
+#else
+#define WF_ENDPATH_ATTR DE_DEV
+#endif
+template <bool COUNT> WF_ENDPATH_ATTR uint32_t end_path(Ctx &c, int slot, uint32_t pk, bool primary_miss, float3 dir);
 template <bool COUNT> DE_DEV uint32_t stage_new(Ctx &c, int slot) {
     const unsigned full = 0xFFFFFFFFu;
     const WfParams &P = c.P;
@@ -424,7 +442,7 @@ template <bool COUNT> DE_DEV uint32_t stage_new(Ctx &c, int slot) {
     return begin_segment(c, slot, PK_SET_LAM(0u, (uint32_t)bin), c.s.cam_pos, dir);
 }
 // pathtracer.py:455-469 + renderer.py:329-330; frees the slot
-template <bool COUNT> DE_DEV uint32_t end_path(Ctx &c, int slot, uint32_t pk, bool primary_miss, float3 dir) {
+template <bool COUNT> WF_ENDPATH_ATTR uint32_t end_path(Ctx &c, int slot, uint32_t pk, bool primary_miss, float3 dir) {
     const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
     float Lr = c.pool.L[slot];
     if (primary_miss) {
@@ -449,23 +467,37 @@ template <bool COUNT> DE_DEV uint32_t end_path(Ctx &c, int slot, uint32_t pk, bo
 // in registers; only when enough lanes idle (or none is busy) are they pushed -- grouped per target
 // queue, one reservation per group -- and the idle lanes refilled from this stage's own queue.
 // Returns the active mask after the refill; lanes that received a slot have take_new = true.
+#ifndef WF_FLUSH_OOL
+#define WF_FLUSH_OOL 1  // the flush / refill path of a burst lives out of line, so the steady-state trip is compact code
+#endif
+// slow path of burst_sync: push the finished lanes, pop replacements.  Returns the slot this lane received, or -1.
+#if WF_FLUSH_OOL
+__device__ __noinline__
+#else
+DE_DEV
+#endif
+int burst_flush(WarpPool &pool, uint32_t st, unsigned am, bool pending, uint32_t pend_st, int pend_slot, int lane) {
+    const unsigned full = 0xFFFFFFFFu;
+    q_push_sorted(pool, pending, pend_st, pend_slot, lane);
+    int av = 0;
+    if (lane == 0) av = *(volatile int *)&pool.q_avail[st];
+    if (__shfl_sync(full, av, 0) <= 0) return -1;  // warp-uniform decision
+    int got_slot;
+    const int n = q_pop(pool, st, 32 - __popc(am), lane, got_slot);
+    if (n == 0) return -1;
+    const int rank = __popc(~am & ((1u << lane) - 1u));
+    const int mine = __shfl_sync(full, got_slot, rank & 31);
+    return (!((am >> lane) & 1u) && rank < n) ? mine : -1;
+}
 DE_DEV unsigned burst_sync(Ctx &c, uint32_t st, bool active, bool &pending, uint32_t pend_st, int pend_slot, int &slot, bool &take_new) {
     const unsigned full = 0xFFFFFFFFu;
     take_new = false;
     unsigned am = __ballot_sync(full, active);
     int idle = 32 - __popc(am);
     if (idle < WF_REFILL_MIN && am != 0u) return am;
-    q_push_sorted(c.pool, pending, pend_st, pend_slot, c.lane);
+    const int got = burst_flush(c.pool, st, am, pending, pend_st, pend_slot, c.lane);
     pending = false;
-    int av = 0;
-    if (c.lane == 0) av = *(volatile int *)&c.pool.q_avail[st];
-    if (__shfl_sync(full, av, 0) <= 0) return am;  // warp-uniform decision
-    int got_slot;
-    int n = q_pop(c.pool, st, idle, c.lane, got_slot);
-    if (n == 0) return am;
-    int rank = __popc(~am & ((1u << c.lane) - 1u));
-    int mine = __shfl_sync(full, got_slot, rank & 31);
-    if (!active && rank < n) { slot = mine; take_new = true; }
+    if (got >= 0) { slot = got; take_new = true; }
     return am | __ballot_sync(full, take_new);
 }
 
@@ -548,7 +580,11 @@ template <bool COUNT> DE_DEV void burst_track(Ctx &c, int slot, const bool IS_CL
     for (int it = 0; it < WF_BURST / 2; ++it) {
         if (active) {
             const bool ratio = (pk & PK_RATIO) != 0u;
+#if WF_TRACK_PHILOX_INLINE
+            const uint4 rb = philox_block_inl(c.P.seed, key1, smp, PK_SC(pk) + 1u, blk);
+#else
             const uint4 rb = philox_block(c.P.seed, key1, smp, PK_SC(pk) + 1u, blk);
+#endif
             bool done = false;
             uint32_t ev = 0u, id = IS_CLOUD ? 3u : 0u, draw_after = 0u;
 #pragma unroll 1
@@ -648,7 +684,10 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
     if (sc > 9u && id == (uint32_t)kCloud) id = kIsoCloud;
     rng.align();
     float3 light_dir = sample_cone_oriented(c.dv.sun_cos_angle, c.dv.light_dir, rng);
-    if (ev == (uint32_t)kAbsorbEvent) return end_path<COUNT>(c, slot, pk, false, d);
+    const float earth_isect = c.pool.isect[slot];
+    const bool absorbed = ev == (uint32_t)kAbsorbEvent;
+    if (absorbed || (ev != (uint32_t)kScatterEvent && !(earth_isect > 0.0f)))  // absorbed, or escaped (pathtracer.py:441-444)
+        return end_path<COUNT>(c, slot, pk, !absorbed && sc == 0u, d);
     if (ev == (uint32_t)kScatterEvent) {
         float3 ipos = o + d * c.pool.t[slot];
         bool blocked = rsi(ipos, light_dir, kPlanetR).y > 0.0f;
@@ -661,8 +700,7 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
         c.pool.isect[slot] = -1.0f;
         return setup_rmo(c, slot, pk, ipos, light_dir, true);
     }
-    float earth_isect = c.pool.isect[slot];
-    if (earth_isect > 0.0f) {
+    {
         DE_COUNT(c.cn, C_SURF);
         float3 land_pos = o + d * earth_isect;
         // land_normal (pathtracer.py:16-25) and get_land_material (:284-313) on the shared fetch routine
@@ -690,7 +728,6 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
         pk |= PK_SURFACE | PK_SHADOW;
         return setup_sdf(c, slot, pk, offset_pos, light_dir, rng.draw);
     }
-    return end_path<COUNT>(c, slot, pk, sc == 0u, d);  // escaped (pathtracer.py:441-444)
 }
 
 // ST_NEE_DONE: after the NEE transmittance, pathtracer.py:394-401 / 431-439, Russian roulette :447-453, next segment

@@ -36,3 +36,25 @@ def render_distributed(renderer, total_spp, rank, world, dst=0):
     reduce_accumulation(renderer.color_buffer, dst)
     renderer.current_spp = total_spp
     return renderer.color_buffer
+
+
+def resolve_fused(renderer, total_spp, rank, world, dst=0):
+    """Exchange step fused into the resolve: `dst` maps the other ranks' accumulation buffers (CUDA IPC over
+    NVLink peer memory) and its resolve kernel sums them while tonemapping -- no reduce pass.  Returns the image on
+    `dst`, None elsewhere.  All ranks must call it; ranks must be processes on one node."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return renderer.fetch_image(spp=total_spp)
+    handles = [None] * world
+    dist.all_gather_object(handles, renderer.export_accum_handle())
+    torch.cuda.synchronize()
+    dist.barrier()                       # every rank's samples are in its buffer
+    img = None
+    if rank == dst:
+        peers = [renderer.open_peer(handles[k]) for k in range(world) if k != dst]
+        img = renderer.fetch_image_peers(peers, total_spp).clone()
+        torch.cuda.synchronize()
+        renderer.close_peers()
+    dist.barrier()                       # the peers' buffers may be reused from here on
+    return img

@@ -47,6 +47,7 @@ def main(argv=None):
     ap.add_argument("--mode", default="wavefront", choices=["wavefront", "megakernel", "parity"])
     ap.add_argument("--tonemapper", default="opendrt", choices=["opendrt", "agx"])
     ap.add_argument("--save-accum", default=None, help=".npz checkpoint of the linear accumulation buffer + spp")
+    ap.add_argument("--resume", default=None, help="continue a still from a --save-accum checkpoint: --spp is the new total")
     a = ap.parse_args(argv)
 
     import numpy as np
@@ -65,8 +66,9 @@ def main(argv=None):
     r.tonemapper = 1 if a.tonemapper == "agx" else 0
     r.copy_textures()
 
-    def render_slice(first, n):
-        r.reset_framebuffer()
+    def render_slice(first, n, keep=False):
+        if not keep:
+            r.reset_framebuffer()
         done = 0
         while done < n:
             k = min(a.batch, n - done)
@@ -81,14 +83,20 @@ def main(argv=None):
             save_screenshot(r.fetch_image(spp=a.spp), os.path.join(a.out_dir, "frame_%04d.png" % f))
     else:
         r.apply_config(cfg)
-        first, n = sample_slice(a.spp, rank, world)
-        render_slice(first, n)
+        have = 0
+        if a.resume:  # rank 0 carries the old sums; every rank renders its share of the NEW samples [have, spp)
+            have = r.load_accumulation(a.resume) if rank == 0 else int(np.load(a.resume)["spp"])
+            if have > a.spp:
+                raise SystemExit("checkpoint already holds %d spp, --spp %d asks for fewer" % (have, a.spp))
+        first, n = sample_slice(a.spp - have, rank, world)
+        render_slice(have + first, n, keep=bool(a.resume) and rank == 0)
         reduce_accumulation(r.color_buffer, dst=0)
         if rank == 0:
+            r.current_spp = a.spp
             img = r.fetch_image(spp=a.spp)
             save_screenshot(img, a.out)
             if a.save_accum:
-                np.savez_compressed(a.save_accum, accum=r.color_buffer.cpu().numpy(), spp=a.spp, config=np.array(list(map(str, cfg.items()))))
+                r.save_accumulation(a.save_accum, extra=cfg)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -249,6 +249,34 @@ class Renderer:
         self._check(self._lib.de_resolve(self._ctx, src, C.c_void_p(self._image.data_ptr()), max(spp, 1)))
         return self._image.permute(1, 0, 2)
 
+    # ---- multi-GPU resolve fused with the accumulation exchange (include/de_api.h) ----
+    def export_accum_handle(self):
+        """64-byte CUDA IPC handle of this rank's accumulation buffer (bytes; send it to the resolving rank)."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.de_ipc_export_accum(self._ctx, buf))
+        return buf.raw
+
+    def open_peer(self, handle):
+        """Map another rank's accumulation buffer (same node) into this process; returns its device address."""
+        ptr = C.c_void_p()
+        self._check(self._lib.de_ipc_open_peer(self._ctx, C.create_string_buffer(bytes(handle), 64), C.byref(ptr)))
+        return ptr.value
+
+    def close_peers(self):
+        self._check(self._lib.de_ipc_close_peers(self._ctx))
+
+    def fetch_image_peers(self, peers, spp):
+        """fetch_image() of (own buffer + the peers' buffers): one kernel reads the other ranks' partial sums over
+        NVLink peer memory while it resolves.  peers: device addresses (open_peer) or CUDA tensors [H][W][3] f32."""
+        if not self._textures_copied:
+            self.copy_textures()
+        self._bind_stream()
+        self._push_params()
+        addrs = [int(p.data_ptr()) if hasattr(p, "data_ptr") else int(p) for p in peers]
+        arr = (C.c_void_p * max(len(addrs), 1))(*addrs)
+        self._check(self._lib.de_resolve_peers(self._ctx, arr, len(addrs), C.c_void_p(self._image.data_ptr()), max(int(spp), 1)))
+        return self._image.permute(1, 0, 2)
+
     @property
     def color_buffer(self):
         """The accumulation buffer (renderer.py:25) as a [H][W][3] float32 CUDA tensor (linear sRGB sums)."""
@@ -256,6 +284,33 @@ class Renderer:
 
     def sync(self):
         self._check(self._lib.de_sync(self._ctx))
+
+    # progressive checkpoint: the linear accumulation buffer + the sample count is the
+    # whole state of a progressive render, because a pixel's sample k is the same path in every launch
+    def save_accumulation(self, path, extra=None):
+        """Write {accum [H][W][3] f32, spp, seed, image_res, params} to an .npz; returns the path."""
+        import numpy as np
+        self.sync()
+        meta = dict(extra or {})
+        np.savez_compressed(path, accum=self._accum.cpu().numpy(), spp=np.int64(self.current_spp), seed=np.int64(self.seed),
+                            image_res=np.asarray(self.image_res, np.int64), meta=np.array(sorted(map(str, meta.items()))))
+        return path if str(path).endswith(".npz") else str(path) + ".npz"
+
+    def load_accumulation(self, path):
+        """Resume from save_accumulation(): the next accumulate() continues at sample index `spp`."""
+        import numpy as np
+        import torch
+        with np.load(path) as z:
+            acc, spp, seed = z["accum"], int(z["spp"]), int(z["seed"]) if "seed" in z else self.seed
+            res = tuple(int(x) for x in z["image_res"]) if "image_res" in z else (acc.shape[1], acc.shape[0])
+        if tuple(res) != tuple(self.image_res) or acc.shape != tuple(self._accum.shape):
+            raise ValueError("checkpoint is %dx%d, renderer is %dx%d" % (res[0], res[1], self.image_res[0], self.image_res[1]))
+        if seed != self.seed:
+            raise ValueError("checkpoint was rendered with seed %d, renderer has seed %d: resuming would repeat or skip sample streams" % (seed, self.seed))
+        self._bind_stream()
+        self._accum.copy_(torch.from_numpy(np.ascontiguousarray(acc, dtype=np.float32)))
+        self.current_spp = spp
+        return spp
 
     def render(self, spp, batch=None):
         """Convenience: reset + accumulate `spp` samples (in batches) + fetch_image."""

@@ -120,6 +120,23 @@ int de_get_accum(de_ctx *ctx, float **dev_ptr);
  * dev_out: device [H][W][3] f32 in [0,1].  accum_override (device, may be NULL) resolves another
  * buffer of the same shape, e.g. an NCCL-reduced one. */
 int de_resolve(de_ctx *ctx, const float *accum_override, float *dev_out, int spp_total);
+/* ---- multi-GPU: resolve fused with the accumulation exchange (one process per GPU) -------------------
+ * The reference is single-device; its film buffer is linear in the samples (renderer.py:329-330), so
+ * ranks that rendered disjoint sample slices only need their buffers SUMMED before _render_to_image
+ * (renderer.py:346-365).  Either reduce them with NCCL and call de_resolve, or let the resolving rank read the
+ * other ranks' buffers in place over NVLink peer memory:
+ *   every rank:      de_ipc_export_accum(ctx, handle)            64-byte CUDA IPC handle of its buffer;
+ *                    exchange the handles (torch.distributed.all_gather_object / any channel);
+ *   resolving rank:  de_ipc_open_peer(ctx, handle_k, &ptr_k)     for every OTHER rank k (same node);
+ *                    de_resolve_peers(ctx, ptrs, n, out, spp)    out = tonemap((own + sum_k ptr_k) / spp);
+ *                    de_ipc_close_peers(ctx).
+ * The other ranks must have finished (stream-synchronised + a barrier) before de_resolve_peers runs and must
+ * keep their buffers untouched until it has completed.  peer pointers may be any device-accessible [H][W][3]
+ * float buffers (IPC-opened, peer-enabled, or on the same device); at most 15. */
+int de_ipc_export_accum(de_ctx *ctx, void *handle64);
+int de_ipc_open_peer(de_ctx *ctx, const void *handle64, float **dev_ptr);
+int de_ipc_close_peers(de_ctx *ctx);
+int de_resolve_peers(de_ctx *ctx, const float *const *peer_accums, int n_peers, float *dev_out, int spp_total);
 /* convenience for non-torch callers: resolve + copy to host memory, synchronous */
 int de_fetch_image_host(de_ctx *ctx, float *host_out, int spp_total);
 int de_sync(de_ctx *ctx);

@@ -212,3 +212,60 @@ def test_headless_cli_writes_an_image(tmp_path):
     rc = render.main(["--config", os.path.join(CFG, "config - florida.txt"), "--res", "64x32", "--spp", "2", "--textures", "synthetic:128x64", "--orbit", "3",
                       "--out-dir", str(tmp_path / "frames")])
     assert rc == 0 and sorted(os.listdir(tmp_path / "frames")) == ["frame_0000.png", "frame_0001.png", "frame_0002.png"]
+
+
+def test_checkpoint_resume_continues_the_same_sample_streams(de, tex, tmp_path):
+    """accum + spp is the whole progressive state; a resumed render equals an uninterrupted one."""
+    r = make(de, tex, "florida", "wavefront")
+    r.reset_framebuffer(); r.accumulate(8)
+    whole = r.color_buffer.cpu().numpy().copy()
+    r.reset_framebuffer(); r.accumulate(3)
+    ck = r.save_accumulation(str(tmp_path / "ck.npz"))
+    r.close()
+    r2 = make(de, tex, "florida", "wavefront")
+    assert r2.load_accumulation(ck) == 3 and r2.current_spp == 3
+    r2.accumulate(5)
+    assert r2.current_spp == 8
+    assert pixel_agreement(r2.color_buffer.cpu().numpy(), whole, rel=1e-4) > 0.999
+    r2.seed += 1
+    with pytest.raises(ValueError):
+        r2.load_accumulation(ck)        # another seed would repeat / skip sample streams
+    r2.close()
+    r3 = de.Renderer((W // 2, H), (0, 1, 0), textures=tex)
+    with pytest.raises(ValueError):
+        r3.load_accumulation(ck)        # another resolution
+    r3.close()
+
+
+def test_cli_resume_matches_a_single_run(tmp_path):
+    from digital_earth_b200 import render
+    cfg = os.path.join(CFG, "config - florida.txt")
+    common = ["--config", cfg, "--res", "128x64", "--textures", "synthetic:256x128"]
+    assert render.main(common + ["--spp", "12", "--out", str(tmp_path / "a.png"), "--save-accum", str(tmp_path / "a.npz")]) == 0
+    assert render.main(common + ["--spp", "4", "--out", str(tmp_path / "b4.png"), "--save-accum", str(tmp_path / "b4.npz")]) == 0
+    assert render.main(common + ["--spp", "12", "--resume", str(tmp_path / "b4.npz"), "--out", str(tmp_path / "b.png"), "--save-accum", str(tmp_path / "b.npz")]) == 0
+    a, b = np.load(tmp_path / "a.npz"), np.load(tmp_path / "b.npz")
+    assert int(a["spp"]) == int(b["spp"]) == 12
+    assert pixel_agreement(b["accum"], a["accum"], rel=1e-4) > 0.999
+
+
+def test_fused_peer_resolve_equals_reduce_then_resolve(de, tex):
+    """SURVEY.md 8e fused variant: the resolve kernel sums other ranks' buffers in place.  One GPU here, so the 'peers'
+    are buffers of the same device; the cross-process IPC path is exercised by bench.py --gpus N --fused-resolve."""
+    import torch
+    from digital_earth_b200 import _lib
+    r = make(de, tex, "florida", "wavefront")
+    parts = []
+    for k in range(3):                                   # three sample slices, as three ranks would render them
+        r.reset_framebuffer(); r.accumulate(2, first_sample=2 * k)
+        parts.append(r.color_buffer.clone())
+    total = parts[0] + parts[1] + parts[2]
+    want = r.fetch_image(accum=total, spp=6).clone()
+    r.color_buffer.copy_(parts[0])
+    got = r.fetch_image_peers([parts[1], parts[2]], 6).clone()
+    assert torch.equal(got, want)                        # same summation order -> bit-identical
+    assert torch.equal(r.fetch_image_peers([], 6), r.fetch_image(accum=parts[0], spp=6))
+    with pytest.raises(_lib.DeError):
+        r.fetch_image_peers([parts[1]] * 16, 6)
+    assert len(r.export_accum_handle()) == 64
+    r.close()
