@@ -53,7 +53,7 @@ static_assert(WF_RING >= WF_SLOTS && (WF_RING & (WF_RING - 1)) == 0 && WF_SLOTS 
 
 // Stages.  Loop stages (SDF, RMO, CLOUD) run bursts of a small loop body; the others are one-shot
 // bodies executed converged over up to 32 slots.  A loop body never runs transition code.
-enum : uint32_t { ST_NEW = 0, ST_SDF, ST_RMO, ST_CLOUD, ST_SDF_DONE, ST_RMO_DONE, ST_EVENT, ST_NEE_DONE, ST_COUNT };
+enum : uint32_t { ST_NEW = 0, ST_SDF, ST_RMO, ST_CLOUD, ST_SDF_DONE, ST_RMO_DONE, ST_EVENT, ST_NEE_DONE, ST_SURFACE, ST_COUNT };
 
 // pk word: stage[0:4) ratio[4] shadow[5] surface[6] vis[7] sc[8:13) lam[13:22) ev[22:24) rmo_ev[24:26) rmo_id[26:28) id[28:31)
 #define PK_STAGE(p) ((p)&15u)
@@ -91,6 +91,7 @@ struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
     int q_avail[ST_COUNT];
     int retired;     // slots that found no more work
     int phase;       // SM-wide preferred stage (WF_PHASE)
+    int starving;    // warps that found every queue empty and are napping (WF_STARVE_FLUSH)
     int work_left;
 };
 
@@ -113,6 +114,9 @@ struct WfParams {
 #endif
 #ifndef WF_CHAIN_TOPUP
 #define WF_CHAIN_TOPUP 4  // idle lanes of a chained group that trigger a top-up from the next stage's queue
+#endif
+#ifndef WF_STARVE_FLUSH
+#define WF_STARVE_FLUSH 0  // >0: a burst pushes its finished lanes as soon as this many are idle while other warps starve
 #endif
 #ifndef WF_OOL_MASK
 #define WF_OOL_MASK 0  // bit 0: end_path out of line, bit 1: setup_sdf out of line
@@ -494,7 +498,17 @@ DE_DEV unsigned burst_sync(Ctx &c, uint32_t st, bool active, bool &pending, uint
     take_new = false;
     unsigned am = __ballot_sync(full, active);
     int idle = 32 - __popc(am);
-    if (idle < WF_REFILL_MIN && am != 0u) return am;
+    if (idle < WF_REFILL_MIN && am != 0u) {
+#if WF_STARVE_FLUSH
+        // finished lanes normally wait for company before they are pushed; not while other warps of the SM have nothing to do
+        if (idle < WF_STARVE_FLUSH) return am;
+        int hungry = 0;
+        if (c.lane == 0) hungry = *(volatile int *)&c.pool.starving;
+        if (__shfl_sync(full, hungry, 0) <= 0) return am;
+#else
+        return am;
+#endif
+    }
     const int got = burst_flush(c.pool, st, am, pending, pend_st, pend_slot, c.lane);
     pending = false;
     if (got >= 0) { slot = got; take_new = true; }
@@ -700,6 +714,21 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
         c.pool.isect[slot] = -1.0f;
         return setup_rmo(c, slot, pk, ipos, light_dir, true);
     }
+    // surface hit: shading is a long body of its own (four height fetches, four material maps, the BRDF) that a
+    // fifth of the events need -- it runs as stage ST_SURFACE over a full group instead of a few lanes of this one
+    c.pool.nx[slot] = light_dir.x; c.pool.ny[slot] = light_dir.y; c.pool.nz[slot] = light_dir.z;
+    store_draw(c, slot, rng.draw, 0u);
+    return PK_SET_STAGE(pk, ST_SURFACE);
+}
+
+// ST_SURFACE: pathtracer.py:405-439 up to the shadow ray -- normal, material, emission, BRDF towards the light
+template <bool COUNT> DE_DEV uint32_t stage_surface(Ctx &c, int slot) {
+    uint32_t pk = c.pool.pk[slot];
+    const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
+    const float3 o = ld_o(c, slot), d = ld_d(c, slot);
+    const float3 light_dir = f3(c.pool.nx[slot], c.pool.ny[slot], c.pool.nz[slot]);
+    const float earth_isect = c.pool.isect[slot];
+    const uint32_t draw = c.pool.draw[slot] & 0xFFFFFFu;
     {
         DE_COUNT(c.cn, C_SURF);
         float3 land_pos = o + d * earth_isect;
@@ -726,7 +755,7 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
         c.pool.mdx[slot] = d.x; c.pool.mdy[slot] = d.y; c.pool.mdz[slot] = d.z;
         st_o(c, slot, offset_pos); st_d(c, slot, light_dir);
         pk |= PK_SURFACE | PK_SHADOW;
-        return setup_sdf(c, slot, pk, offset_pos, light_dir, rng.draw);
+        return setup_sdf(c, slot, pk, offset_pos, light_dir, draw);
     }
 }
 
@@ -793,7 +822,7 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         pool.q_head[threadIdx.x] = 0u;
         pool.q_avail[threadIdx.x] = threadIdx.x == ST_NEW ? WF_SLOTS : 0;
     }
-    if (threadIdx.x == 0) { pool.retired = 0; pool.work_left = 1; pool.phase = 0; }
+    if (threadIdx.x == 0) { pool.retired = 0; pool.work_left = 1; pool.phase = 0; pool.starving = 0; }
     __syncthreads();
     int last_st = -1;
     bool chained = false;  // the warp already holds slots of stage `st` (handed over by the previous one-shot stage)
@@ -823,7 +852,13 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
             if (key == 0) {
                 if (wl & 2) break;  // every slot found the work counter exhausted
                 long long t0i = COUNT ? clock64() : 0;
+#if WF_STARVE_FLUSH
+                if (lane == 0) atomicAdd(&pool.starving, 1);
                 __nanosleep(WF_BACKOFF_NS > 64 ? WF_BACKOFF_NS : 64);
+                if (lane == 0) atomicSub(&pool.starving, 1);
+#else
+                __nanosleep(WF_BACKOFF_NS > 64 ? WF_BACKOFF_NS : 64);
+#endif
                 if (COUNT && lane == 0 && P.prof) atomicAdd(&P.prof[3 * ST_COUNT], (unsigned long long)(clock64() - t0i));
                 continue;
             }
@@ -868,6 +903,7 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
                 if (st == ST_SDF_DONE) npk = stage_sdf_done(c, slot);
                 else if (st == ST_RMO_DONE) npk = stage_rmo_done(c, slot);
                 else if (st == ST_EVENT) npk = stage_event<COUNT>(c, slot);
+                else if (st == ST_SURFACE) npk = stage_surface<COUNT>(c, slot);
                 else npk = stage_nee_done<COUNT>(c, slot);
             }
             if (has) c.pool.pk[slot] = npk;

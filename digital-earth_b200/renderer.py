@@ -141,9 +141,9 @@ class Renderer:
         import numpy as np
         buf = np.zeros(32, np.uint64)
         self._check(self._lib.de_get_stage_profile(self._ctx, buf.ctypes.data_as(C.c_void_p)))
-        names = ("NEW", "SDF", "RMO", "CLOUD", "SDF_DONE", "RMO_DONE", "EVENT", "NEE_DONE")
+        names = ("NEW", "SDF", "RMO", "CLOUD", "SDF_DONE", "RMO_DONE", "EVENT", "NEE_DONE", "SURFACE")
         out = {n: tuple(int(x) for x in buf[3 * i:3 * i + 3]) for i, n in enumerate(names)}
-        out["IDLE"] = (int(buf[24]), 0, 0)
+        out["IDLE"] = (int(buf[3 * len(names)]), 0, 0)
         return out
 
     def _bind_stream(self):

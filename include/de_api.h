@@ -143,7 +143,7 @@ int de_sync(de_ctx *ctx);
 int de_get_counters(de_ctx *ctx, DeCounters *out); /* synchronises */
 int de_set_counting(de_ctx *ctx, int enabled);     /* counters cost atomics: off by default */
 /* scheduler self-profile of the last counting de_accumulate (wavefront mode): out32[3*s+{0,1,2}] = warp cycles,
- * visits and slots handled by stage s (NEW, SDF, RMO, CLOUD, SDF_DONE, RMO_DONE, EVENT, NEE_DONE), out32[24] = idle cycles */
+ * visits and slots handled by stage s (NEW, SDF, RMO, CLOUD, SDF_DONE, RMO_DONE, EVENT, NEE_DONE, SURFACE), out32[27] = idle cycles */
 int de_get_stage_profile(de_ctx *ctx, uint64_t *out32);
 
 /* ---- test hooks: the deterministic sub-paths of SURVEY 8(a), DEVICE pointers, n items --------

@@ -836,6 +836,109 @@ static float path_tracer(const orc_scene *s, const scene_params *sc, float wavel
     return in_scattering;
 }
 
+/* ------------------------------------------ deterministic preview integrator -- */
+/* pathtracer.py:471-499: 16-step optical depth towards the light; 0 when the planet is in the way */
+static float ray_march_transmittance(v3 ray_pos, v3 ray_dir, v3 rmo_ext) {
+    const int steps = 16;
+    float r_steps = 1.0f / (float)steps;
+    float transmittance = 0.0f;
+    int visibility = rsi(ray_pos, ray_dir, PLANET_R).y > 0.0f;
+    if (!visibility) {
+        v2 atm = rsi(ray_pos, ray_dir, ATMOS_UPPER);
+        float t_max = atm.y;
+        if (atm.y < 0.0f) t_max = -1.0f;
+        float dd = t_max * r_steps;
+        v3 ray_step = scl3(ray_dir, dd);
+        v3 od = V3(0.0f, 0.0f, 0.0f);
+        for (int i = 0; i < steps; ++i) {
+            v3 density = get_density(get_elevation(ray_pos));
+            od = add3(od, scl3(density, dd));
+            ray_pos = add3(ray_pos, ray_step);
+        }
+        transmittance = expf(-dot3(rmo_ext, od));
+    }
+    return transmittance;
+}
+/* pathtracer.py:501-541: 64-step single scattering of Rayleigh + Mie along the view segment */
+static void ray_march_atmos(v3 ray_pos, v3 ray_dir, float t_start, float t_max, v3 sun_dir, v3 rmo_ext, v2 rm_scat,
+                            float *in_scatter_out, float *transmittance_out) {
+    const int steps = 64;
+    float r_steps = 1.0f / (float)steps;
+    float dd = (t_max - t_start) * r_steps;
+    v3 ray_step = scl3(ray_dir, dd);
+    ray_pos = add3(ray_pos, scl3(ray_dir, t_start));
+    float cos_theta = dot3(ray_dir, sun_dir);
+    float ph_r = rayleigh_phase(cos_theta), ph_m = mie_phase(cos_theta);
+    float transmittance = 1.0f, in_scatter = 0.0f;
+    for (int i = 0; i < steps; ++i) {
+        float h = get_elevation(ray_pos);
+        v3 density = get_density(h);
+        float step_od = dot3(rmo_ext, scl3(density, dd));
+        float step_T = saturate(expf(-step_od));
+        float step_integral = saturate((1.0f - step_T) / step_od);
+        float visible = transmittance * step_integral;
+        float sun_T = ray_march_transmittance(ray_pos, sun_dir, rmo_ext);
+        float step_scat = rm_scat.x * (density.x * ph_r) + rm_scat.y * (density.y * ph_m); /* vec2.dot */
+        in_scatter += step_scat * sun_T * visible * dd;
+        transmittance *= step_T;
+        ray_pos = add3(ray_pos, ray_step);
+    }
+    *in_scatter_out = in_scatter; *transmittance_out = transmittance;
+}
+/* pathtracer.py:543-685 (dead code upstream; kept as a noise-free preview).  RNG: the light-cone sample and the
+ * hemisphere sample each start on a multiple of 4 of ONE stream (bounce key 1) for the whole path. */
+static float ray_marcher(const orc_scene *s, const scene_params *sc, float wavelength, v3 ray_pos, v3 ray_dir, orc_rng *r, orc_counters *cnt) {
+    const v3 path_ray_dir = ray_dir;
+    float sun_power = plancks(5778.0f, wavelength);
+    float nightlights_power = plancks(2700.0f, wavelength) * 0.0001f;
+    float sun_irradiance = sun_power * cone_angle_to_solid_angle(sc->sun_angular_radius);
+    v3 ext = V3(spectra_extinction_rayleigh(wavelength), spectra_extinction_mie(wavelength), spectra_extinction_ozone(wavelength, s->o3));
+    v2 scat; scat.x = ext.x * RAYLEIGH_ALBEDO; scat.y = ext.y * AEROSOL_ALBEDO;
+    int primary_miss = 0;
+    float accum = 0.0f, throughput = 1.0f;
+    rng_bounce(r, 1u);
+    for (int scatter_count = 0; scatter_count < 3; ++scatter_count) {
+        float earth_isect = intersect_land(s, ray_pos, ray_dir, sc->land_height_scale, cnt);
+        v2 atm = rsi(ray_pos, ray_dir, ATMOS_UPPER);
+        float t_start = fmaxf(0.0f, atm.x);
+        float t_max = earth_isect > 0.0f ? earth_isect : atm.y;
+        if (atm.y < 0.0f) { primary_miss = scatter_count == 0; break; }
+        rng_align(r);
+        v3 light_dir = sample_cone_oriented(sc->sun_cos_angle, sc->light_direction, r);
+        float in_scatter, transmittance;
+        ray_march_atmos(ray_pos, ray_dir, t_start, t_max, light_dir, ext, scat, &in_scatter, &transmittance);
+        accum += throughput * in_scatter;
+        throughput *= transmittance;
+        if (earth_isect > 0.0f) {
+            v3 land_pos = add3(ray_pos, scl3(ray_dir, earth_isect));
+            v3 nrm = land_normal(s, land_pos, sc->land_height_scale, cnt);
+            land_material m = get_land_material(s, land_pos, cnt);
+            float albedo = srgb_to_spectrum(s->srgb2spec, m.albedo_srgb, wavelength);
+            accum += throughput * m.emissive * nightlights_power;
+            v3 offset_pos = scl3(land_pos, 1.0f + 0.0001f * sc->land_height_scale / 12000.0f);
+            int vis = intersect_land(s, offset_pos, light_dir, sc->land_height_scale, cnt) < 0.0f;
+            float ndl;
+            float dbrdf = earth_brdf(albedo, m.ocean, m.bathymetry, neg3(ray_dir), nrm, light_dir, &ndl);
+            accum += throughput * 1.0f * (float)vis * sun_irradiance * dbrdf * ndl;
+            v3 view_dir = neg3(ray_dir);
+            rng_align(r);
+            ray_dir = sample_hemisphere_cosine_weighted(nrm, r);
+            ray_pos = offset_pos;
+            float unused;
+            float brdf = earth_brdf(albedo, m.ocean, m.bathymetry, view_dir, nrm, ray_dir, &unused);
+            throughput *= brdf * PI_F;
+        }
+    }
+    if (primary_miss) {
+        if (dot3(sc->light_direction, path_ray_dir) > sc->sun_cos_angle) accum += sun_power;
+        texel4 st = sample_sphere_texture(&s->tex[T_STARS], path_ray_dir, cnt);
+        float stars_power = srgb_to_spectrum(s->srgb2spec, V3(st.c[0], st.c[1], st.c[2]), wavelength);
+        accum += stars_power * sun_power * 0.0000001f;
+    }
+    if (isinf(accum) || isnan(accum) || accum < 0.0f) accum = 0.0f;
+    return accum;
+}
+
 /* colour.py:12-48 */
 static void spectrum_sample(const float *cie, float sample, float *wavelength, v3 *response, float *rcp_pdf) {
     float lo = 0.0f, hi = 1.0f, mid = (lo + hi) / 2.0f;
