@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--res", default="1920x1080")
     ap.add_argument("--spp", type=int, default=1024)
     ap.add_argument("--tex", default="8192x4096")
-    ap.add_argument("--mode", default="wavefront", choices=["wavefront", "megakernel", "parity"])
+    ap.add_argument("--mode", default="wavefront", choices=["wavefront", "megakernel", "parity", "preview"])
     ap.add_argument("--cpu-res", default="480x272")
     ap.add_argument("--cpu-spp", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")

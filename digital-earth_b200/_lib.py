@@ -7,7 +7,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DE_LIB_PATH") or os.path.join(_HERE, "libde.so")  # DE_LIB_PATH: tuning builds
 
 DE_MODE_WAVEFRONT, DE_MODE_MEGAKERNEL, DE_MODE_PARITY = 0, 1, 2
-MODES = {"wavefront": DE_MODE_WAVEFRONT, "megakernel": DE_MODE_MEGAKERNEL, "parity": DE_MODE_PARITY}
+DE_MODE_PREVIEW = 3
+MODES = {"wavefront": DE_MODE_WAVEFRONT, "megakernel": DE_MODE_MEGAKERNEL, "parity": DE_MODE_PARITY, "preview": DE_MODE_PREVIEW}
 TEX_SLOTS = ("albedo", "topography", "ocean", "clouds", "bathymetry", "emissive", "stars")
 
 
@@ -81,6 +82,8 @@ _SIGS = {
     "de_test_raymarch_T": ([_P, _P, _P, _P, _P, _I], _I),
     "de_test_tracking": ([_P, _I, _P, _P, _P, _P, _U, _P, _I], _I),
     "de_test_trace_paths": ([_P, _P, _P, _P, _U, _P, _I], _I),
+    "de_test_trace_preview": ([_P, _P, _P, _P, _U, _P, _I], _I),
+    "de_test_ray_march": ([_P, _P, _P, _P, _P, _P, _P, _P, _I], _I),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -142,7 +142,7 @@ int de_set_stream(de_ctx *ctx, void *cuda_stream) {
 }
 int de_set_mode(de_ctx *ctx, int mode) {
     ENTER();
-    NEED(mode >= DE_MODE_WAVEFRONT && mode <= DE_MODE_PARITY, "unknown mode");
+    NEED(mode >= DE_MODE_WAVEFRONT && mode <= DE_MODE_PREVIEW, "unknown mode");
     ctx->mode = mode;
     return DE_OK;
 }
@@ -257,6 +257,7 @@ int de_accumulate(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, 
     int rc = ready_to_render(ctx);
     if (rc) return rc;
     if (ctx->mode == DE_MODE_PARITY) de_exact::launch_render_mega(ctx->scene, ctx->d_accum, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
+    else if (ctx->mode == DE_MODE_PREVIEW) de_fast::launch_render_preview(ctx->scene, ctx->d_accum, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
     else if (ctx->mode == DE_MODE_MEGAKERNEL) de_fast::launch_render_mega(ctx->scene, ctx->d_accum, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
     else {
         if (!ctx->wf) {
@@ -396,6 +397,17 @@ int de_test_cloud_limits(de_ctx *ctx, const float *pos, const float *dir, const 
 int de_test_clouds_density(de_ctx *ctx, const float *pos, float *out, int n) { HOOK_PRE(true); de_exact::t_clouds_density(ctx->scene, pos, out, n, ctx->stream); HOOK_POST("clouds_density"); }
 int de_test_raymarch_T(de_ctx *ctx, const float *pos, const float *dir, const float *ext, float *out, int n) { HOOK_PRE(false); de_exact::t_raymarch_T(pos, dir, ext, out, n, ctx->stream); HOOK_POST("raymarch_T"); }
 int de_test_tracking(de_ctx *ctx, int kind, const float *pos, const float *dir, const float *land, const float *wl, uint32_t seed, float *out, int n) { HOOK_PRE(true); de_exact::t_tracking(ctx->scene, kind, pos, dir, land, wl, seed, out, n, ctx->stream); HOOK_POST("tracking"); }
+int de_test_ray_march(de_ctx *ctx, const float *pos, const float *dir, const float *t0, const float *t1, const float *sun, const float *wl, float *out2, int n) {
+    HOOK_PRE(true); de_exact::t_ray_march(ctx->scene, pos, dir, t0, t1, sun, wl, out2, n, ctx->stream); HOOK_POST("ray_march");
+}
+int de_test_trace_preview(de_ctx *ctx, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out, int n) {
+    ENTER();
+    if (n <= 0) return DE_OK;
+    int rc = ready_to_render(ctx);
+    if (rc) return rc;
+    de_exact::t_trace_preview(ctx->scene, px, py, sample, seed, out, n, ctx->stream);
+    HOOK_POST("trace_preview");
+}
 int de_test_trace_paths(de_ctx *ctx, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out, int n) {
     ENTER();
     if (n <= 0) return DE_OK;

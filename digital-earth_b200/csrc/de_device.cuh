@@ -34,6 +34,7 @@ constexpr float kCloudsThickness = 6000.0f;
 constexpr float kCloudsExtinct = 0.1f;
 constexpr float kCloudsDensity = 0.029f;
 constexpr float kMieAsymmetry = 3000.0f;
+constexpr float kRayleighAlbedo = 1.0f, kAerosolAlbedo = 0.95f;  // volume_rendering_models.py:27-28
 constexpr float kPi = 3.14159265358979323846f;
 constexpr float kTwoPi = 6.28318530717958647692f;
 constexpr float kFourPi = 12.56637061435917295385f;

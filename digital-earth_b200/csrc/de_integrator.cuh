@@ -277,8 +277,111 @@ DE_DEV float path_tracer(const DevScene &s, const DevDerived &dv, const LambdaRo
     return in_scattering;
 }
 
+// ------------------------------------------------------------------ deterministic preview
+// pathtracer.py:471-499: 16-step optical depth towards the light; 0 when the planet is in the way
+DE_DEV float ray_march_transmittance(float3 pos, float3 dir, float3 ext) {
+    const int steps = 16;
+    const float r_steps = 1.0f / (float)steps;
+    float T = 0.0f;
+    const bool visibility = rsi(pos, dir, kPlanetR).y > 0.0f;
+    if (!visibility) {
+        float2 atm = rsi(pos, dir, kAtmosUpper);
+        float t_max = atm.y;
+        if (atm.y < 0.0f) t_max = -1.0f;
+        const float dd = t_max * r_steps;
+        const float3 step = dir * dd;
+        float3 od = f3(0.0f, 0.0f, 0.0f);
+        for (int k = 0; k < steps; ++k) {
+            float3 d = get_density(get_elevation(pos));
+            od = od + d * dd;
+            pos = pos + step;
+        }
+        T = expf(-dot(ext, od));
+    }
+    return T;
+}
+// pathtracer.py:501-541: 64-step single scattering (Rayleigh + Mie) over [t_start, t_max]
+DE_DEV void ray_march_atmos(float3 pos, float3 dir, float t_start, float t_max, float3 sun_dir, float3 ext, float2 scat, float &in_scatter, float &transmittance) {
+    const int steps = 64;
+    const float r_steps = 1.0f / (float)steps;
+    const float dd = (t_max - t_start) * r_steps;
+    const float3 step = dir * dd;
+    pos = pos + dir * t_start;
+    const float cos_theta = dot(dir, sun_dir);
+    const float ph_r = rayleigh_phase(cos_theta), ph_m = klein_nishina_phase(cos_theta, kMieAsymmetry);
+    transmittance = 1.0f;
+    in_scatter = 0.0f;
+#pragma unroll 1
+    for (int i = 0; i < steps; ++i) {
+        float3 density = get_density(get_elevation(pos));
+        float step_od = dot(ext, density * dd);
+        float step_T = saturate(expf(-step_od));
+        float step_integral = saturate((1.0f - step_T) / step_od);
+        float visible = transmittance * step_integral;
+        float sun_T = ray_march_transmittance(pos, sun_dir, ext);
+        float step_scat = scat.x * (density.x * ph_r) + scat.y * (density.y * ph_m);
+        in_scatter += step_scat * sun_T * visible * dd;
+        transmittance *= step_T;
+        pos = pos + step;
+    }
+}
+// pathtracer.py:543-685 (unreferenced upstream): <= 3 surface bounces, marched atmosphere, no clouds.  One random stream
+// for the whole path (bounce key 1); the light-cone and hemisphere samples start on multiples of 4.
+template <bool COUNT, class R>
+DE_DEV float ray_marcher(const DevScene &s, const DevDerived &dv, const LambdaRow &lr, float3 ray_pos, float3 ray_dir, R &rng, Counters &cn) {
+    const float3 path_ray_dir = ray_dir;
+    const float3 ext = f3(lr.ext_r, lr.ext_m, lr.ext_o);
+    const float2 scat = make_float2(lr.ext_r * kRayleighAlbedo, lr.ext_m * kAerosolAlbedo);
+    bool primary_miss = false;
+    float accum = 0.0f, throughput = 1.0f;
+    rng.set_bounce(1u);
+    for (int scatter_count = 0; scatter_count < 3; ++scatter_count) {
+        DE_COUNT(cn, C_SEGMENTS);
+        float earth_isect = intersect_land<COUNT>(s, ray_pos, ray_dir, s.land_height_scale, cn);
+        float2 atm = rsi(ray_pos, ray_dir, kAtmosUpper);
+        float t_start = fmaxf(0.0f, atm.x);
+        float t_max = earth_isect > 0.0f ? earth_isect : atm.y;
+        if (atm.y < 0.0f) { primary_miss = scatter_count == 0; break; }
+        rng.align();
+        float3 light_dir = sample_cone_oriented(dv.sun_cos_angle, dv.light_dir, rng);
+        float in_scatter, transmittance;
+        ray_march_atmos(ray_pos, ray_dir, t_start, t_max, light_dir, ext, scat, in_scatter, transmittance);
+        accum += throughput * in_scatter;
+        throughput *= transmittance;
+        if (earth_isect > 0.0f) {
+            DE_COUNT(cn, C_SURF);
+            float3 land_pos = ray_pos + ray_dir * earth_isect;
+            float3 nrm = land_normal<COUNT>(s, dv.normal_eps, land_pos, s.land_height_scale, cn);
+            LandMaterial m = get_land_material<COUNT>(s, land_pos, cn);
+            float albedo = lr.s2s_valid != 0.0f ? dot(m.albedo_srgb, f3(lr.s2s_r, lr.s2s_g, lr.s2s_b)) : 0.0f;
+            accum += throughput * m.emissive * lr.nightlights_power;
+            float3 offset_pos = land_pos * (1.0f + 0.0001f * s.land_height_scale / 12000.0f);
+            bool vis = intersect_land<COUNT>(s, offset_pos, light_dir, s.land_height_scale, cn) < 0.0f;
+            float ndl;
+            float dbrdf = earth_brdf(albedo, m.ocean, m.bathymetry, -ray_dir, nrm, light_dir, ndl);
+            accum += throughput * 1.0f * (vis ? 1.0f : 0.0f) * lr.sun_irradiance * dbrdf * ndl;
+            float3 view_dir = -ray_dir;
+            rng.align();
+            ray_dir = sample_hemisphere_cosine_weighted(nrm, rng);
+            ray_pos = offset_pos;
+            float unused;
+            float brdf = earth_brdf(albedo, m.ocean, m.bathymetry, view_dir, nrm, ray_dir, unused);
+            throughput *= brdf * kPi;
+        }
+    }
+    if (primary_miss) {
+        if (dot(dv.light_dir, path_ray_dir) > dv.sun_cos_angle) accum += lr.sun_power;
+        DE_COUNT(cn, C_TEX);
+        float3 st = sample_sphere_rgb8(s.tex[6], path_ray_dir);
+        float stars_power = lr.s2s_valid != 0.0f ? dot(st, f3(lr.s2s_r, lr.s2s_g, lr.s2s_b)) : 0.0f;
+        accum += stars_power * lr.sun_power * 0.0000001f;
+    }
+    if (isinf(accum) || isnan(accum) || accum < 0.0f) accum = 0.0f;
+    return accum;
+}
+
 // renderer.py:305-330: one path sample for pixel (u,v) -> linear sRGB contribution
-template <bool COUNT>
+template <bool COUNT, bool PREVIEW = false>
 DE_DEV float3 render_sample(const DevScene &s, const DevDerived &dv, int u, int v, uint32_t sample_index, uint32_t seed, Counters &cn, float *wl_out, float *L_out) {
     Rng rng;
     rng.init(seed, (uint32_t)(v * s.W + u), sample_index);
@@ -286,7 +389,7 @@ DE_DEV float3 render_sample(const DevScene &s, const DevDerived &dv, int u, int 
     LambdaRow lr = s.lam[bin];
     float xu = rng.next(), xv = rng.next();
     float3 dir = get_cast_dir(s, dv, (float)u, (float)v, xu, xv);
-    float L = path_tracer<COUNT>(s, dv, lr, s.cam_pos, dir, rng, cn);
+    float L = PREVIEW ? ray_marcher<COUNT>(s, dv, lr, s.cam_pos, dir, rng, cn) : path_tracer<COUNT>(s, dv, lr, s.cam_pos, dir, rng, cn);
     if (COUNT) { cn.v[C_PATHS]++; }
     if (wl_out) *wl_out = lr.wavelength;
     if (L_out) *L_out = L;

@@ -11,7 +11,7 @@ namespace DE_NS {
 
 // Renderer.render (renderer.py:283-330): one thread per pixel, a 16x8 film tile per 128-thread
 // CTA as in renderer.py:43-46,304; n_spp samples per launch instead of one.
-template <bool COUNT>
+template <bool COUNT, bool PREVIEW>
 __global__ void __launch_bounds__(128) k_render_mega(DevScene s, float *__restrict__ accum, int n_spp, uint32_t seed, uint32_t first_sample,
                                                     int x0, int y0, int w, int h) {
     int tiles_x = (w + kDeTileW - 1) / kDeTileW;
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128) k_render_mega(DevScene s, float *__restri
     size_t k = ((size_t)py * s.W + px) * 3;
     float3 acc = f3(accum[k], accum[k + 1], accum[k + 2]);
     for (int sp = 0; sp < n_spp; ++sp) {
-        float3 c = render_sample<COUNT>(s, dv, px, py, first_sample + (uint32_t)sp, seed, cn, nullptr, nullptr);
+        float3 c = render_sample<COUNT, PREVIEW>(s, dv, px, py, first_sample + (uint32_t)sp, seed, cn, nullptr, nullptr);
         acc = acc + c;
     }
     accum[k] = acc.x; accum[k + 1] = acc.y; accum[k + 2] = acc.z;
@@ -32,8 +32,15 @@ __global__ void __launch_bounds__(128) k_render_mega(DevScene s, float *__restri
 }
 void launch_render_mega(const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, bool count, cudaStream_t st) {
     int tiles = ((w + kDeTileW - 1) / kDeTileW) * ((h + kDeTileH - 1) / kDeTileH);
-    if (count) k_render_mega<true><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
-    else k_render_mega<false><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
+    if (count) k_render_mega<true, false><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
+    else k_render_mega<false, false><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
+}
+// the deterministic ray-marching preview (pathtracer.py:543-685) on the same film layout: every lane runs the same
+// 64 x 16 fixed-step loops, so one thread per pixel is already converged
+void launch_render_preview(const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, bool count, cudaStream_t st) {
+    int tiles = ((w + kDeTileW - 1) / kDeTileW) * ((h + kDeTileH - 1) / kDeTileH);
+    if (count) k_render_mega<true, true><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
+    else k_render_mega<false, true><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
 }
 
 // Renderer._render_to_image (renderer.py:346-365)
@@ -274,17 +281,7 @@ void t_clouds_density(const DevScene &s, const float *pos, float *out, int n, cu
 
 // pathtracer.py:471-500
 HOOK_BEGIN(raymarch_T, const float *pos_, const float *dir_, const float *ext_, float *out)
-    float3 pos = LD3(pos_, i), dir = LD3(dir_, i), ext = LD3(ext_, i);
-    const int steps = 16; float r_steps = 1.0f / (float)steps, T = 0.0f;
-    bool visibility = rsi(pos, dir, kPlanetR).y > 0.0f;
-    if (!visibility) {
-        float2 atm = rsi(pos, dir, kAtmosUpper);
-        float t_max = atm.y; if (atm.y < 0.0f) t_max = -1.0f;
-        float dd = t_max * r_steps; float3 step = dir * dd, od = f3(0, 0, 0);
-        for (int k = 0; k < steps; ++k) { float3 d = get_density(get_elevation(pos)); od = od + d * dd; pos = pos + step; }
-        T = expf(-dot(ext, od));
-    }
-    out[i] = T;
+    out[i] = ray_march_transmittance(LD3(pos_, i), LD3(dir_, i), LD3(ext_, i));
 HOOK_END
 void t_raymarch_T(const float *pos, const float *dir, const float *ext, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(raymarch_T, n, st, pos, dir, ext, out); }
 
@@ -297,6 +294,22 @@ HOOK_BEGIN(tracking, DevScene s, int kind, const float *pos, const float *dir, c
     else { out[3 * i] = sample_transmittance<false>(s, LD3(pos, i), LD3(dir, i), land[i], ext, kCloudsExtinct, mr, mc, r, cn); out[3 * i + 1] = 0.0f; out[3 * i + 2] = 0.0f; }
 HOOK_END
 void t_tracking(const DevScene &s, int kind, const float *pos, const float *dir, const float *land, const float *wl, uint32_t seed, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(tracking, n, st, s, kind, pos, dir, land, wl, seed, out); }
+
+// pathtracer.py:501-541 on explicit rays: out2 = (in_scatter, transmittance)
+HOOK_BEGIN(ray_march, DevScene s, const float *pos, const float *dir, const float *t0, const float *t1, const float *sun, const float *wl, float *out2)
+    float3 ext = f3(spectra_extinction_rayleigh(wl[i]), spectra_extinction_mie(wl[i]), spectra_extinction_ozone(wl[i], s.o3));
+    float a, b;
+    ray_march_atmos(LD3(pos, i), LD3(dir, i), t0[i], t1[i], LD3(sun, i), ext, make_float2(ext.x * kRayleighAlbedo, ext.y * kAerosolAlbedo), a, b);
+    out2[2 * i] = a; out2[2 * i + 1] = b;
+HOOK_END
+void t_ray_march(const DevScene &s, const float *pos, const float *dir, const float *t0, const float *t1, const float *sun, const float *wl, float *out2, int n, cudaStream_t st) { HOOK_LAUNCH(ray_march, n, st, s, pos, dir, t0, t1, sun, wl, out2); }
+
+HOOK_BEGIN(trace_preview, DevScene s, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out)
+    Counters cn; DevDerived dv = *s.derived; float wl, L;
+    float3 c = render_sample<false, true>(s, dv, px[i], py[i], sample[i], seed, cn, &wl, &L);
+    out[5 * i] = c.x; out[5 * i + 1] = c.y; out[5 * i + 2] = c.z; out[5 * i + 3] = wl; out[5 * i + 4] = L;
+HOOK_END
+void t_trace_preview(const DevScene &s, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out, int n, cudaStream_t st) { HOOK_LAUNCH(trace_preview, n, st, s, px, py, sample, seed, out); }
 
 HOOK_BEGIN(trace_paths, DevScene s, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out)
     Counters cn; DevDerived dv = *s.derived; float wl, L;

@@ -8,6 +8,8 @@ constexpr int kDeMaxPeers = 15;  // other ranks whose accumulation buffers one r
 #define DE_DECLARE_COMMON                                                                                                              \
     void launch_render_mega(const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w,  \
                             int h, bool count, cudaStream_t st);                                                                       \
+    void launch_render_preview(const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0,      \
+                               int w, int h, bool count, cudaStream_t st);                                                            \
     void launch_resolve(const DevScene &s, const float *accum, float *out, int spp, cudaStream_t st);                                 \
     void launch_resolve_peers(const DevScene &s, const float *accum, const float *const *peers, int n_peers, float *out, int spp,     \
                               cudaStream_t st);
@@ -44,5 +46,7 @@ void t_cloud_limits(const float *pos, const float *dir, const float *land, float
 void t_clouds_density(const DevScene &s, const float *pos, float *out, int n, cudaStream_t st);
 void t_raymarch_T(const float *pos, const float *dir, const float *ext, float *out, int n, cudaStream_t st);
 void t_tracking(const DevScene &s, int kind, const float *pos, const float *dir, const float *land, const float *wl, uint32_t seed, float *out, int n, cudaStream_t st);
+void t_ray_march(const DevScene &s, const float *pos, const float *dir, const float *t0, const float *t1, const float *sun, const float *wl, float *out2, int n, cudaStream_t st);
+void t_trace_preview(const DevScene &s, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out, int n, cudaStream_t st);
 void t_trace_paths(const DevScene &s, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out, int n, cudaStream_t st);
 }  // namespace de_exact

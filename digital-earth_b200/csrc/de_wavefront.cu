@@ -91,7 +91,6 @@ struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
     int q_avail[ST_COUNT];
     int retired;     // slots that found no more work
     int phase;       // SM-wide preferred stage (WF_PHASE)
-    int starving;    // warps that found every queue empty and are napping (WF_STARVE_FLUSH)
     int work_left;
 };
 
@@ -114,9 +113,6 @@ struct WfParams {
 #endif
 #ifndef WF_CHAIN_TOPUP
 #define WF_CHAIN_TOPUP 4  // idle lanes of a chained group that trigger a top-up from the next stage's queue
-#endif
-#ifndef WF_STARVE_FLUSH
-#define WF_STARVE_FLUSH 0  // >0: a burst pushes its finished lanes as soon as this many are idle while other warps starve
 #endif
 #ifndef WF_OOL_MASK
 #define WF_OOL_MASK 0  // bit 0: end_path out of line, bit 1: setup_sdf out of line
@@ -498,17 +494,7 @@ DE_DEV unsigned burst_sync(Ctx &c, uint32_t st, bool active, bool &pending, uint
     take_new = false;
     unsigned am = __ballot_sync(full, active);
     int idle = 32 - __popc(am);
-    if (idle < WF_REFILL_MIN && am != 0u) {
-#if WF_STARVE_FLUSH
-        // finished lanes normally wait for company before they are pushed; not while other warps of the SM have nothing to do
-        if (idle < WF_STARVE_FLUSH) return am;
-        int hungry = 0;
-        if (c.lane == 0) hungry = *(volatile int *)&c.pool.starving;
-        if (__shfl_sync(full, hungry, 0) <= 0) return am;
-#else
-        return am;
-#endif
-    }
+    if (idle < WF_REFILL_MIN && am != 0u) return am;
     const int got = burst_flush(c.pool, st, am, pending, pend_st, pend_slot, c.lane);
     pending = false;
     if (got >= 0) { slot = got; take_new = true; }
@@ -822,7 +808,7 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         pool.q_head[threadIdx.x] = 0u;
         pool.q_avail[threadIdx.x] = threadIdx.x == ST_NEW ? WF_SLOTS : 0;
     }
-    if (threadIdx.x == 0) { pool.retired = 0; pool.work_left = 1; pool.phase = 0; pool.starving = 0; }
+    if (threadIdx.x == 0) { pool.retired = 0; pool.work_left = 1; pool.phase = 0; }
     __syncthreads();
     int last_st = -1;
     bool chained = false;  // the warp already holds slots of stage `st` (handed over by the previous one-shot stage)
@@ -852,13 +838,7 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
             if (key == 0) {
                 if (wl & 2) break;  // every slot found the work counter exhausted
                 long long t0i = COUNT ? clock64() : 0;
-#if WF_STARVE_FLUSH
-                if (lane == 0) atomicAdd(&pool.starving, 1);
                 __nanosleep(WF_BACKOFF_NS > 64 ? WF_BACKOFF_NS : 64);
-                if (lane == 0) atomicSub(&pool.starving, 1);
-#else
-                __nanosleep(WF_BACKOFF_NS > 64 ? WF_BACKOFF_NS : 64);
-#endif
                 if (COUNT && lane == 0 && P.prof) atomicAdd(&P.prof[3 * ST_COUNT], (unsigned long long)(clock64() - t0i));
                 continue;
             }

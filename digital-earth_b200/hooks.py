@@ -77,4 +77,6 @@ class Hooks:
     def clouds_density(self, pos): return self._call("de_test_clouds_density", len(pos), (len(pos),), self.f(pos))
     def raymarch_T(self, pos, d, ext): return self._call("de_test_raymarch_T", len(pos), (len(pos),), self.f(pos), self.f(d), self.f(ext))
     def tracking(self, kind, pos, d, land, wl, seed): return self._call("de_test_tracking", len(land), (len(land), 3), int(kind), self.f(pos), self.f(d), self.f(land), self.f(wl), C.c_uint32(seed))
+    def trace_preview(self, px, py, sample, seed): return self._call("de_test_trace_preview", len(px), (len(px), 5), self.i(px), self.i(py), self.u(sample), C.c_uint32(seed))
+    def ray_march(self, pos, direction, t0, t1, sun, wl): return self._call("de_test_ray_march", len(pos), (len(pos), 2), self.f(pos), self.f(direction), self.f(t0), self.f(t1), self.f(sun), self.f(wl))
     def trace_paths(self, px, py, sample, seed): return self._call("de_test_trace_paths", len(px), (len(px), 5), self.i(px), self.i(py), self.u(sample), C.c_uint32(seed))

@@ -44,7 +44,7 @@ def main(argv=None):
     ap.add_argument("--orbit", type=int, default=0, help="render N frames of an orbit instead of one still")
     ap.add_argument("--degrees-per-frame", type=float, default=3.0)
     ap.add_argument("--out-dir", default="frames")
-    ap.add_argument("--mode", default="wavefront", choices=["wavefront", "megakernel", "parity"])
+    ap.add_argument("--mode", default="wavefront", choices=["wavefront", "megakernel", "parity", "preview"])
     ap.add_argument("--tonemapper", default="opendrt", choices=["opendrt", "agx"])
     ap.add_argument("--save-accum", default=None, help=".npz checkpoint of the linear accumulation buffer + spp")
     ap.add_argument("--resume", default=None, help="continue a still from a --save-accum checkpoint: --spp is the new total")

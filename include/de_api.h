@@ -54,8 +54,11 @@ enum { DE_TEX_ALBEDO = 0, DE_TEX_TOPOGRAPHY, DE_TEX_OCEAN, DE_TEX_CLOUDS, DE_TEX
 enum {
     DE_MODE_WAVEFRONT = 0, /* product path: persistent-thread, stage-sorted, FMA + fast intrinsics */
     DE_MODE_MEGAKERNEL = 1,/* one thread per pixel, same fast arithmetic (baseline for profiles)   */
-    DE_MODE_PARITY = 2     /* one thread per pixel, IEEE source-order arithmetic (no FMA
+    DE_MODE_PARITY = 2,    /* one thread per pixel, IEEE source-order arithmetic (no FMA
                               contraction, accurate libm): comparable to the oracle per path       */
+    DE_MODE_PREVIEW = 3    /* deterministic ray-marching integrator `ray_marcher` (pathtracer.py:543-685,
+                              unreferenced upstream): 64-step view march x 16-step sun march, <= 3 surface
+                              bounces, no clouds -- a noise-free atmosphere preview; fast arithmetic   */
 };
 
 typedef struct de_ctx de_ctx;
@@ -173,6 +176,8 @@ int de_test_raymarch_T(de_ctx *, const float *pos3, const float *dir3, const flo
 /* kind 0: sample_interaction -> (event, t, id); kind 1: sample_transmittance -> (T, 0, 0); Philox key (seed, i), bounce 1 */
 int de_test_tracking(de_ctx *, int kind, const float *pos3, const float *dir3, const float *land, const float *wavelength, uint32_t seed, float *out3, int n); /* pathtracer.py:172,211 */
 /* individual path samples in PARITY arithmetic: out5 = rgb contribution, wavelength, radiance   renderer.py:305-330 */
+int de_test_ray_march(de_ctx *, const float *pos3, const float *dir3, const float *t0, const float *t1, const float *sun3, const float *wavelength, float *out2, int n); /* pathtracer.py:501-541 */
+int de_test_trace_preview(de_ctx *, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out5, int n); /* renderer.py:305-330 with pathtracer.py:543-685 */
 int de_test_trace_paths(de_ctx *, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out5, int n);
 
 #if defined(__GNUC__)

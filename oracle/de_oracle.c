@@ -155,6 +155,8 @@ static const float TWO_PI_F = (float)(2.0 * 3.141592653589793);
 #define CLOUDS_EXTINCT 0.1f
 #define CLOUDS_DENSITY 0.029f
 #define MIE_ASYMMETRY 3000.0f
+#define RAYLEIGH_ALBEDO 1.0f /* volume_rendering_models.py:27-28 */
+#define AEROSOL_ALBEDO 0.95f
 enum { RAYLEIGH_ID = 0, MIE_ID = 1, OZONE_ID = 2, CLOUD_ID = 3, ISOTROPIC_CLOUD_ID = 4 };
 enum { NULL_EVENT = 0, ABSORB_EVENT = 1, SCATTER_EVENT = 2 };
 
@@ -326,6 +328,8 @@ static float rayleigh_phase(float c) { return (float)(3.0 / (16.0 * 3.1415926535
 static float klein_nishina_phase(float c, float e) {
     return e / (TWO_PI_F * (e * (1.0f - c) + 1.0f) * logf(2.0f * e + 1.0f));
 }
+/* :65-67 */
+static float mie_phase(float c) { return klein_nishina_phase(c, MIE_ASYMMETRY); }
 /* :73-75 */
 static float hg_phase(float c, float g) {
     return (1 - g * g) / ((float)(4.0 * 3.141592653589793) * pow_ti(1.0f + g * g - 2 * g * c, 1.5f));
@@ -837,7 +841,8 @@ static float path_tracer(const orc_scene *s, const scene_params *sc, float wavel
 }
 
 /* ------------------------------------------ deterministic preview integrator -- */
-/* pathtracer.py:471-499: 16-step optical depth towards the light; 0 when the planet is in the way */
+/* pathtracer.py:471-499: 16-step optical depth towards the light; 0 when the planet is in the way
+ * (also a deterministic test vehicle on its own: orc_raymarch_T) */
 static float ray_march_transmittance(v3 ray_pos, v3 ray_dir, v3 rmo_ext) {
     const int steps = 16;
     float r_steps = 1.0f / (float)steps;
@@ -978,8 +983,15 @@ static const float XYZ2RGB[9] = { (float)3.2409699419, (float)-1.5373831776, (fl
                                   (float)-0.9692436363, (float)1.8759675015, (float)0.0415550574,
                                   (float)0.0556300797, (float)-0.2039769589, (float)1.0569715142 };
 /* renderer.py:305-330: one path sample for pixel (u,v) -> linear sRGB contribution */
+static v3 render_sample2(const orc_scene *s, const scene_params *sc, int u, int v, uint32_t sample_index, uint32_t seed,
+                         orc_counters *cnt, float *wl_out, float *L_out, int integrator);
 static v3 render_sample(const orc_scene *s, const scene_params *sc, int u, int v, uint32_t sample_index, uint32_t seed,
                         orc_counters *cnt, float *wl_out, float *L_out) {
+    return render_sample2(s, sc, u, v, sample_index, seed, cnt, wl_out, L_out, 0);
+}
+/* integrator: 0 = path_tracer (what renderer.py:317 calls), 1 = ray_marcher (the preview) */
+static v3 render_sample2(const orc_scene *s, const scene_params *sc, int u, int v, uint32_t sample_index, uint32_t seed,
+                         orc_counters *cnt, float *wl_out, float *L_out, int integrator) {
     orc_rng r; memset(&r, 0, sizeof r);
     r.key0 = seed; r.key1 = (uint32_t)(v * s->W + u); r.sample = sample_index; r.cnt = cnt;
     rng_bounce(&r, 0);
@@ -988,7 +1000,7 @@ static v3 render_sample(const orc_scene *s, const scene_params *sc, int u, int v
     float xu = rnd(&r), xv = rnd(&r);
     v3 dir = get_cast_dir(s, (float)u, (float)v, xu, xv);
     v3 pos = V3(s->cam_pos[0], s->cam_pos[1], s->cam_pos[2]);
-    float L = path_tracer(s, sc, wl, pos, dir, &r, cnt);
+    float L = integrator == 1 ? ray_marcher(s, sc, wl, pos, dir, &r, cnt) : path_tracer(s, sc, wl, pos, dir, &r, cnt);
     if (cnt) cnt->paths++;
     v3 xyz = scl3(scl3(resp, L), rcp);
     if (wl_out) *wl_out = wl;
@@ -1182,27 +1194,6 @@ static v3 resolve_pixel(const orc_scene *s, int i, int j, v3 color, int samples)
     return V3(srgb_transfer1(g.x), srgb_transfer1(g.y), srgb_transfer1(g.z));
 }
 
-/* pathtracer.py:471-500 -- deterministic fixed-ray transmittance (test vehicle) */
-static float ray_march_transmittance(v3 pos, v3 dir, v3 ext) {
-    int steps = 16;
-    float r_steps = 1.0f / (float)steps, T = 0.0f;
-    int visibility = rsi(pos, dir, PLANET_R).y > 0.0f;
-    if (!visibility) {
-        v2 atm = rsi(pos, dir, ATMOS_UPPER);
-        float t_max = atm.y;
-        if (atm.y < 0.0f) t_max = -1.0f;
-        float dd = t_max * r_steps;
-        v3 step = scl3(dir, dd), od = V3(0, 0, 0);
-        for (int i = 0; i < steps; ++i) {
-            v3 d = get_density(get_elevation(pos));
-            od = add3(od, scl3(d, dd));
-            pos = add3(pos, step);
-        }
-        T = expf(-dot3(ext, od));
-    }
-    return T;
-}
-
 /* ================================================================= API ==
  * Batch entry points (ctypes).  All arrays are caller-owned host memory. */
 #define LD3(p, i) V3((p)[3 * (i)], (p)[3 * (i) + 1], (p)[3 * (i) + 2])
@@ -1312,11 +1303,28 @@ ORC_API void orc_trace_paths(const orc_scene *s, int n, const int32_t *px, const
     for (int i = 0; i < n; ++i) { v3 c = render_sample(s, &sc, px[i], py[i], sample[i], seed, cnt, &out[5 * i + 3], &out[5 * i + 4]); out[5 * i] = c.x; out[5 * i + 1] = c.y; out[5 * i + 2] = c.z; }
 }
 
+ORC_API void orc_trace_paths2(const orc_scene *s, int n, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out, orc_counters *cnt, int integrator) {
+    scene_params sc = make_scene_params(s);
+    for (int i = 0; i < n; ++i) { v3 c = render_sample2(s, &sc, px[i], py[i], sample[i], seed, cnt, &out[5 * i + 3], &out[5 * i + 4], integrator); out[5 * i] = c.x; out[5 * i + 1] = c.y; out[5 * i + 2] = c.z; }
+}
+/* the preview's two marching routines on explicit inputs (pathtracer.py:471-541): out[n][2] = (in_scatter, transmittance) of
+ * ray_marh_atmos over [t0[i], t1[i]] with light direction sun[i]; outT[n] = ray_march_transmittance(pos, sun) */
+ORC_API void orc_ray_march(const orc_scene *s, int n, const float *pos, const float *dir, const float *t0, const float *t1, const float *sun,
+                           const float *wl, float *out2, float *outT) {
+    for (int i = 0; i < n; ++i) {
+        v3 ext = V3(spectra_extinction_rayleigh(wl[i]), spectra_extinction_mie(wl[i]), spectra_extinction_ozone(wl[i], s->o3));
+        v2 scat; scat.x = ext.x * RAYLEIGH_ALBEDO; scat.y = ext.y * AEROSOL_ALBEDO;
+        v3 p = V3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), d = V3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), l = V3(sun[3 * i], sun[3 * i + 1], sun[3 * i + 2]);
+        ray_march_atmos(p, d, t0[i], t1[i], l, ext, scat, &out2[2 * i], &out2[2 * i + 1]);
+        outT[i] = ray_march_transmittance(p, l, ext);
+    }
+}
+
 /* Multi-threaded render (the CPU baseline): accum[y][x][3] += spp samples per pixel in the
  * window [x0,x0+w) x [y0,y0+h); optional accum2 accumulates squared luminance-like moments per channel. */
 typedef struct {
     const orc_scene *s; scene_params sc; int x0, y0, w, h, spp; uint32_t first_sample, seed;
-    float *accum, *accum2; volatile int32_t *next_row; orc_counters cnt;
+    float *accum, *accum2; volatile int32_t *next_row; orc_counters cnt; int integrator;
 } render_job;
 static void *render_worker(void *arg) {
     render_job *j = (render_job *)arg;
@@ -1327,7 +1335,7 @@ static void *render_worker(void *arg) {
         for (int x = j->x0; x < j->x0 + j->w; ++x) {
             size_t k = ((size_t)y * j->s->W + x) * 3;
             for (int sp = 0; sp < j->spp; ++sp) {
-                v3 c = render_sample(j->s, &j->sc, x, y, j->first_sample + (uint32_t)sp, j->seed, &j->cnt, NULL, NULL);
+                v3 c = render_sample2(j->s, &j->sc, x, y, j->first_sample + (uint32_t)sp, j->seed, &j->cnt, NULL, NULL, j->integrator);
                 j->accum[k] += c.x; j->accum[k + 1] += c.y; j->accum[k + 2] += c.z;
                 if (j->accum2) { j->accum2[k] += c.x * c.x; j->accum2[k + 1] += c.y * c.y; j->accum2[k + 2] += c.z * c.z; }
             }
@@ -1335,8 +1343,14 @@ static void *render_worker(void *arg) {
     }
     return NULL;
 }
+ORC_API void orc_render2(const orc_scene *s, int x0, int y0, int w, int h, int spp, uint32_t first_sample, uint32_t seed,
+                         float *accum, float *accum2, int nthreads, orc_counters *cnt_out, int integrator);
 ORC_API void orc_render(const orc_scene *s, int x0, int y0, int w, int h, int spp, uint32_t first_sample, uint32_t seed,
                         float *accum, float *accum2, int nthreads, orc_counters *cnt_out) {
+    orc_render2(s, x0, y0, w, h, spp, first_sample, seed, accum, accum2, nthreads, cnt_out, 0);
+}
+ORC_API void orc_render2(const orc_scene *s, int x0, int y0, int w, int h, int spp, uint32_t first_sample, uint32_t seed,
+                         float *accum, float *accum2, int nthreads, orc_counters *cnt_out, int integrator) {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     volatile int32_t next_row = 0;
@@ -1346,7 +1360,7 @@ ORC_API void orc_render(const orc_scene *s, int x0, int y0, int w, int h, int sp
     for (int t = 0; t < nthreads; ++t) {
         render_job *j = &jobs[t];
         j->s = s; j->sc = sc; j->x0 = x0; j->y0 = y0; j->w = w; j->h = h; j->spp = spp; j->first_sample = first_sample; j->seed = seed;
-        j->accum = accum; j->accum2 = accum2; j->next_row = &next_row;
+        j->accum = accum; j->accum2 = accum2; j->next_row = &next_row; j->integrator = integrator;
         pthread_create(&th[t], NULL, render_worker, j);
     }
     orc_counters tot; memset(&tot, 0, sizeof tot);

@@ -272,16 +272,28 @@ def tracking(kind, scene, pos, dirs, land, wl, seed):
     return out
 
 
-def trace_paths(scene, px, py, sample, seed, counters=False):
+INTEGRATORS = {"path_tracer": 0, "ray_marcher": 1}  # pathtracer.py:316 (what the renderer calls) / :543 (the preview)
+
+
+def trace_paths(scene, px, py, sample, seed, counters=False, integrator="path_tracer"):
     px, py = np.ascontiguousarray(px, np.int32), np.ascontiguousarray(py, np.int32)
     sm = np.ascontiguousarray(sample, np.uint32)
     out = np.zeros((len(px), 5), np.float32)
     cnt = OrcCounters()
-    lib().orc_trace_paths(scene.ref, C.c_int(len(px)), _p(px), _p(py), _p(sm), C.c_uint32(seed), _p(out), C.byref(cnt))
+    lib().orc_trace_paths2(scene.ref, C.c_int(len(px)), _p(px), _p(py), _p(sm), C.c_uint32(seed), _p(out), C.byref(cnt), C.c_int(INTEGRATORS[integrator]))
     return (out, cnt.as_dict()) if counters else out
 
 
-def render(scene, spp, first_sample=0, seed=0, window=None, nthreads=None, second_moment=False):
+def ray_march(scene, pos, direction, t0, t1, sun, wavelength):
+    """(in_scatter, transmittance) of ray_marh_atmos and ray_march_transmittance(pos, sun) per row (pathtracer.py:471-541)."""
+    pos, direction, sun = (np.ascontiguousarray(a, np.float32) for a in (pos, direction, sun))
+    t0, t1, wl = (np.ascontiguousarray(a, np.float32) for a in (t0, t1, wavelength))
+    out2, outT = np.zeros((len(pos), 2), np.float32), np.zeros(len(pos), np.float32)
+    lib().orc_ray_march(scene.ref, C.c_int(len(pos)), _p(pos), _p(direction), _p(t0), _p(t1), _p(sun), _p(wl), _p(out2), _p(outT))
+    return out2, outT
+
+
+def render(scene, spp, first_sample=0, seed=0, window=None, nthreads=None, second_moment=False, integrator="path_tracer"):
     """accum[H][W][3] (+ optional squared-sum buffer) and the event counters."""
     W, H = scene.s.W, scene.s.H
     x0, y0, w, h = window or (0, 0, W, H)
@@ -289,6 +301,7 @@ def render(scene, spp, first_sample=0, seed=0, window=None, nthreads=None, secon
     accum2 = np.zeros((H, W, 3), np.float32) if second_moment else None
     cnt = OrcCounters()
     nthreads = nthreads or os.cpu_count() or 1
-    lib().orc_render(scene.ref, C.c_int(x0), C.c_int(y0), C.c_int(w), C.c_int(h), C.c_int(spp), C.c_uint32(first_sample),
-                     C.c_uint32(seed), _p(accum), _p(accum2) if second_moment else None, C.c_int(nthreads), C.byref(cnt))
+    lib().orc_render2(scene.ref, C.c_int(x0), C.c_int(y0), C.c_int(w), C.c_int(h), C.c_int(spp), C.c_uint32(first_sample),
+                      C.c_uint32(seed), _p(accum), _p(accum2) if second_moment else None, C.c_int(nthreads), C.byref(cnt),
+                      C.c_int(INTEGRATORS[integrator]))
     return (accum, accum2, cnt.as_dict()) if second_moment else (accum, cnt.as_dict())

@@ -19,6 +19,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_preview():
+    """outputs of the reference's ray_marcher (pathtracer.py:471-685), tests/golden/gen_golden_preview.py"""
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_preview_v1.npz"))
+
+
+@pytest.fixture(scope="session")
 def luts():
     from oracle import oracle as orc
     return orc.load_luts()

@@ -209,6 +209,12 @@ def test_headless_cli_writes_an_image(tmp_path):
     assert rc == 0
     im = np.array(Image.open(out))
     assert im.shape == (64, 128, 3) and im.max() > 20
+    out2 = str(tmp_path / "florida_preview.png")
+    rc = render.main(["--config", os.path.join(CFG, "config - florida.txt"), "--res", "128x64", "--spp", "4", "--textures", "synthetic:256x128", "--mode", "preview", "--out", out2])
+    assert rc == 0
+    im2 = np.array(Image.open(out2)).astype(np.float32)
+    assert im2.shape == (64, 128, 3) and im2.max() > 20
+    assert np.abs(im2.mean() - im.astype(np.float32).mean()) < 40   # the cloud-free preview shows the same planet, not the same picture
     rc = render.main(["--config", os.path.join(CFG, "config - florida.txt"), "--res", "64x32", "--spp", "2", "--textures", "synthetic:128x64", "--orbit", "3",
                       "--out-dir", str(tmp_path / "frames")])
     assert rc == 0 and sorted(os.listdir(tmp_path / "frames")) == ["frame_0000.png", "frame_0001.png", "frame_0002.png"]

@@ -147,3 +147,21 @@ def test_full_paths(golden, key):
     s = tiny_scene(g, key)
     out = orc.trace_paths(s, g["path_%s_px" % key], g["path_%s_py" % key], g["path_%s_sample" % key], int(g["path_seed"]))
     same(out, g["path_%s_out" % key])
+
+
+# ---- the deterministic preview integrator: the reference's ray_marcher, executed on the stand-in
+def test_preview_marching_routines(golden, golden_preview):
+    gp = golden_preview
+    s = tiny_scene(golden, "florida")
+    atmos, T = orc.ray_march(s, gp["rm_pos"], gp["rm_dir"], gp["rm_t0"], gp["rm_t1"], gp["rm_sun"], gp["rm_wl"])
+    same(atmos, gp["rm_atmos_out"])   # pathtracer.py:501-541
+    same(T, gp["rm_T_out"])           # pathtracer.py:471-499
+
+
+@pytest.mark.parametrize("key", ["apollo", "florida", "sunset"])
+def test_preview_full_samples(golden, golden_preview, key):
+    gp = golden_preview
+    out = orc.trace_paths(tiny_scene(golden, key), gp["prev_%s_px" % key], gp["prev_%s_py" % key], gp["prev_%s_sample" % key], int(gp["prev_seed"]),
+                          integrator="ray_marcher")
+    same(out, gp["prev_%s_out" % key])
+    assert (gp["prev_%s_out" % key][:, 4] > 0).sum() >= 20   # the vectors are not all space background

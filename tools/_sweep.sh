@@ -1,6 +1,4 @@
 cd $GRAFT_REPO_ROOT
-for v in "" _sf1 _sf3 _sf3bo256 _bo256 _w24 _w28; do
-  echo "=== variant libde$v"
-  DE_LIB_PATH=$PWD/digital-earth_b200/libde$v.so timeout 300 python tools/quick_bench.py --res 1920x1080 --spp 16 --modes wavefront 2>&1 | grep -v "^scene"
-done > gpurun_out/sweep7.log 2>&1
-tail -40 gpurun_out/sweep7.log
+timeout 900 python -m pytest tests -x -q -m gpu -k "preview or cli or library" > gpurun_out/sweep9_tests.log 2>&1
+timeout 600 python tools/quick_bench.py --res 1920x1080 --spp 4 --modes preview,wavefront --scenes florida > gpurun_out/sweep9.log 2>&1
+tail -15 gpurun_out/sweep9_tests.log; tail -5 gpurun_out/sweep9.log
