@@ -149,7 +149,7 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "%s, %dx%d, %d spp, synthetic %s textures" % (SCENES[a.scene], W, H, a.spp, a.tex), "scene": a.scene,
+        "config": {"workload": "%s (config - %s.txt), %dx%d, %d spp, synthetic %s textures" % (a.scene, SCENES[a.scene], W, H, a.spp, a.tex), "scene": a.scene,
                    "note": "CPU arm renders a bounded sample of this workload per step: " + sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

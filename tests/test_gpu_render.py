@@ -275,3 +275,39 @@ def test_fused_peer_resolve_equals_reduce_then_resolve(de, tex):
         r.fetch_image_peers([parts[1]] * 16, 6)
     assert len(r.export_accum_handle()) == 64
     r.close()
+
+
+def test_nasa_resolution_textures(de):
+    """the maps the reference ships with are 21600 x 10800 (lib/textures.py:1-79).  Synthetic maps
+    are blown up to that size; fetches and whole paths must still follow the oracle (index arithmetic beyond 2^28
+    texels, 233 MB r8 / 933 MB rgba arrays), and the product integrator must agree with the parity one."""
+    import torch
+    from digital_earth_b200.hooks import Hooks
+    from oracle import oracle as orc
+    base = de.textures.synthetic(2700, 1350, cloud_cover=0.5, seed=5)
+    tex = {k: np.ascontiguousarray(np.repeat(np.repeat(v, 8, axis=0), 8, axis=1)) for k, v in base.items()}
+    assert tex["clouds"].shape == (10800, 21600) and tex["albedo"].shape == (10800, 21600, 3)
+    cfg = de.load_config(os.path.join(CFG, "config - florida.txt"))
+    r = de.Renderer((64, 32), (0, 1, 0), textures=tex, mode="parity")
+    r.apply_config(cfg)
+    r.copy_textures()
+    h = Hooks(r)
+    rng = np.random.default_rng(9)
+    pos = rng.normal(size=(4096, 3)).astype(np.float32)
+    pos[:8] = [[-1, 0, 1e-7], [-1, 0, -1e-7], [0, 1, 0], [0, -1, 0], [1, 0, 0], [-1, 1e-7, 0], [0, 0, 1], [0, 0, -1]]   # date line, poles
+    pos *= 6371e3
+    for slot, name in ((3, "clouds"), (1, "topography"), (0, "albedo")):
+        got, want = h.tex_fetch(slot, pos), orc.tex_fetch(tex[name], pos)
+        assert np.abs(got - want).max() <= 2e-5, (name, np.abs(got - want).max())
+    s = orc.Scene(tex, 64, 32, cam_pos=cfg["cam_pos"], look_at=cfg["look_at"], up=cfg["up"], fov=cfg["fov"], aspect_scale=cfg["aspect_scale"], exposure=cfg["exposure"],
+                  selected_crf=cfg["selected_crf"], gamma=cfg["gamma"], sun_angle=cfg["sun_angle"], sun_path_rot=cfg["sun_path_rot"])
+    px, py, sm = rng.integers(0, 64, 256), rng.integers(0, 32, 256), rng.integers(0, 4, 256)
+    got, want = h.trace_paths(px, py, sm, 7), orc.trace_paths(s, px, py, sm, 7)
+    sc = np.maximum(np.abs(want), np.abs(want).max() * 1e-6)
+    assert ((np.abs(got - want) <= 1e-4 * sc).all(axis=1)).mean() > 0.9
+    r.set_mode("parity"); r.reset_framebuffer(); r.accumulate(64); a = r.color_buffer.clone()
+    r.set_mode("wavefront"); r.reset_framebuffer(); r.accumulate(64); b = r.color_buffer.clone()
+    assert abs(float(a.sum() - b.sum())) <= 0.05 * float(a.sum())       # 131 k paths each: a few per cent of noise
+    r.close()
+    del tex
+    torch.cuda.empty_cache()
