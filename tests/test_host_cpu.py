@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -199,3 +200,19 @@ def test_lut_provenance(luts):
     assert prov["ozone_regenerated_bit_exact"] and prov["srgb2spec_regenerated_bit_exact"]
     for k in ("cie", "srgb2spec", "o3", "crf"):
         assert hashlib.sha256(np.ascontiguousarray(luts[k]).tobytes()).hexdigest() == prov["sha256_" + k], k
+
+
+def test_oracle_event_fixture_feeds_the_roofline_model():
+    """bench.py's FLOP model uses the oracle's event counts of each bench view (profiles/oracle_events.json)."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    ev = json.load(open(os.path.join(ROOT, "profiles", "oracle_events.json")))
+    for key, lo, hi in (("apollo_8192x4096", 5e3, 8e3), ("florida_2048x1024", 1.4e4, 2.2e4), ("sunset_8192x4096", 2.8e4, 4.2e4)):
+        assert lo < bench.flop_per_path(ev[key]) < hi, key
+
+    class A:
+        scene, tex = "apollo", "8192x4096"
+    assert bench.oracle_events(A)["paths"] > 0
+    A.tex = "123x45"
+    assert bench.oracle_events(A) is None
