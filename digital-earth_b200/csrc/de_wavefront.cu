@@ -418,8 +418,9 @@ template <bool COUNT> DE_DEV uint32_t stage_new(Ctx &c, int slot) {
     if (c.lane == 0) chunk = atomicAdd(P.next, 1u);
     chunk = __shfl_sync(full, chunk, 0);
     if (chunk >= P.n_chunks) return ~0u;
-    unsigned index = chunk * 32u + (unsigned)c.lane;
-    unsigned in_tile = index & 127u, ts = index >> 7;
+    // chunk = (tile * n_spp + sample) * 4 + quarter; kept in chunk units: the path index itself exceeds 32 bits for
+    // 4K x 4096 spp (3.4e10 paths)
+    unsigned in_tile = (chunk & 3u) * 32u + (unsigned)c.lane, ts = chunk >> 2;
     unsigned sp = ts % (unsigned)P.n_spp, tile = ts / (unsigned)P.n_spp;
     int px = P.x0 + (int)(tile % (unsigned)P.tiles_x) * kDeTileW + (int)(in_tile & 15u);
     int py = P.y0 + (int)(tile / (unsigned)P.tiles_x) * kDeTileH + (int)(in_tile >> 4);
@@ -963,15 +964,21 @@ void de_wavefront_render(DeWavefrontState *st, const DevScene &s, float *accum, 
     WfParams P;
     P.accum = accum; P.next = st->d_next;
     P.tiles_x = (w + kDeTileW - 1) / kDeTileW;
-    int tiles = P.tiles_x * ((h + kDeTileH - 1) / kDeTileH);
-    P.n_chunks = (unsigned)tiles * (unsigned)n_spp * 4u;
-    P.n_spp = n_spp; P.x0 = x0; P.y0 = y0; P.w = w; P.h = h; P.seed = seed; P.first_sample = first_sample;
-    cudaMemsetAsync(st->d_next, 0, sizeof(unsigned int), stream);
+    const long long tiles = (long long)P.tiles_x * ((h + kDeTileH - 1) / kDeTileH);
+    P.x0 = x0; P.y0 = y0; P.w = w; P.h = h; P.seed = seed;
     P.prof = count ? st->d_prof : nullptr;
     if (count) cudaMemsetAsync(st->d_prof, 0, sizeof(unsigned long long) * 32, stream);
-    int grid = st->sm_count;
-    if (count) k_render_wavefront<true><<<grid, WF_WARPS * 32, smem, stream>>>(s, P);
-    else k_render_wavefront<false><<<grid, WF_WARPS * 32, smem, stream>>>(s, P);
+    // the work counter is 32 bits wide: at most 2^31 chunks (2^36 paths) per launch, more samples go in several launches
+    const long long max_spp = ((1LL << 31) / (tiles * 4) > 1) ? (1LL << 31) / (tiles * 4) : 1;
+    for (long long done = 0; done < n_spp; done += max_spp) {
+        const int batch = (int)((n_spp - done < max_spp) ? n_spp - done : max_spp);
+        P.n_chunks = (unsigned)(tiles * batch * 4);
+        P.n_spp = batch; P.first_sample = first_sample + (uint32_t)done;
+        cudaMemsetAsync(st->d_next, 0, sizeof(unsigned int), stream);
+        const int grid = st->sm_count;
+        if (count) k_render_wavefront<true><<<grid, WF_WARPS * 32, smem, stream>>>(s, P);
+        else k_render_wavefront<false><<<grid, WF_WARPS * 32, smem, stream>>>(s, P);
+    }
 }
 
 int de_wavefront_profile(DeWavefrontState *st, unsigned long long *out32) {

@@ -77,10 +77,19 @@ def main(argv=None):
 
     if a.orbit:
         os.makedirs(a.out_dir, exist_ok=True)
-        for f in frame_shard(a.orbit, rank, world):
+        mine, dev_ms = frame_shard(a.orbit, rank, world), 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for f in mine:
             r.apply_config(orbit_config(cfg, math.radians(a.degrees_per_frame * f)))
+            e0.record()
             render_slice(0, a.spp)
-            save_screenshot(r.fetch_image(spp=a.spp), os.path.join(a.out_dir, "frame_%04d.png" % f))
+            img = r.fetch_image(spp=a.spp)
+            e1.record()
+            save_screenshot(img, os.path.join(a.out_dir, "frame_%04d.png" % f))
+            dev_ms += e0.elapsed_time(e1)
+        if mine:
+            print("rank %d: %d frames of %dx%d x %d spp, %.1f ms/frame on the device (%.2f frames/s, %.1f M samples/s)"
+                  % (rank, len(mine), W, H, a.spp, dev_ms / len(mine), 1e3 * len(mine) / dev_ms, W * H * a.spp * len(mine) / dev_ms / 1e3), flush=True)
     else:
         r.apply_config(cfg)
         have = 0

@@ -313,3 +313,20 @@ def test_nasa_resolution_textures(de):
     r.close()
     del tex
     torch.cuda.empty_cache()
+
+
+def test_more_than_2_to_the_32_paths_in_one_call(de, tex):
+    """BASELINE configs[3] (4K x 4096 spp) is 3.4e10 paths per frame: the work distribution must not wrap at 2^32.  A camera that
+    looks away from the planet makes every path a primary miss (stars), so 5.2e9 paths take about a second."""
+    r = de.Renderer((1024, 1024), (0, 1, 0), textures=tex)
+    r.set_camera_pos(0.0, 0.0, 3.0e7); r.set_look_at(0.0, 0.0, 6.0e7)
+    spp = 5000                                           # 1024 * 1024 * 5000 = 5.24e9 > 2^32
+    r.reset_framebuffer(); r.accumulate(spp)
+    whole = r.color_buffer.clone()
+    r.reset_framebuffer(); r.accumulate(spp // 2); r.accumulate(spp - spp // 2)     # 2.6e9 paths per call
+    halves = r.color_buffer.clone()
+    assert float(whole.sum()) > 0.0
+    assert float((whole - halves).abs().max()) <= 1e-3 * float(whole.abs().max())
+    lit = whole.sum(dim=-1) > 0
+    assert bool((lit == (halves.sum(dim=-1) > 0)).all())  # the same pixels received light
+    r.close()
