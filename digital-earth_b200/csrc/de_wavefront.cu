@@ -5,14 +5,17 @@
 // (L1 97 %, L2 98 % hits, DRAM idle).  This kernel keeps every lane of a warp inside the SAME
 // inner loop:
 //   * one persistent CTA per SM owns a pool of WF_SLOTS path states in shared memory (SoA,
-//     108 B per path), so path state never touches HBM;
+//     112 B per path), so path state never touches HBM;
 //   * a path is a small state machine  SDF -> SDF_DONE -> RMO -> RMO_DONE -> CLOUD -> EVENT ->
-//     (SDF ->) RMO -> CLOUD -> NEE_DONE -> SDF ...  (pathtracer.py:349-453 cut at its loop
-//     boundaries); every stage has a ring queue of ready slots in shared memory;
-//   * a warp pops up to 32 slots of the fullest queue and runs that stage with all lanes converged:
-//     loop stages (SDF / RMO / CLOUD) in bursts, refilling idle lanes from the same queue, the
-//     transition and shading stages as one-shot bodies; a finished lane only records its result
-//     and pushes the slot to the next stage's queue (warp-aggregated where the stage is one-shot);
+//     (SURFACE -> SDF ->) RMO -> RMO_DONE -> CLOUD -> NEE_DONE -> SDF ...  (pathtracer.py:349-453 cut
+//     at its loop boundaries); every stage has a ring queue of ready slots in shared memory;
+//   * a warp pops up to 32 slots of one queue -- the stage the whole SM is working on while that has a
+//     full group (the instruction caches then hold one body), else the fullest -- and runs the stage
+//     with all lanes converged: loop stages (SDF / RMO / CLOUD) in bursts, refilling idle lanes from
+//     the same queue, the transition and shading stages as one-shot bodies; a finished lane only
+//     records its result and pushes the slot to the next stage's queue (one reservation per group);
+//   * code size is throughput here (profiles/r1_bench.md): one copy of every large helper per stage,
+//     cold math out of line, no dead fallback paths;
 //   * terminated paths free their slot; free slots are refilled 32 at a time from a global atomic
 //     work counter (path regeneration): 32 neighbouring pixels of one 16x8 film tile, one sample.
 // The random stream of a path is the contract of include/de_api.h (Philox key (seed,pixel), counter
@@ -25,7 +28,7 @@
 namespace de_fast {
 
 #ifndef WF_SLOTS
-#define WF_SLOTS 1728  // path states per CTA (one CTA per SM): 189 KB of state (28 words each) + 32 KB of queues
+#define WF_SLOTS 1728  // path states per CTA (one CTA per SM): 189 KB of state (28 words each) + 36 KB of queues
 #endif
 #ifndef WF_WARPS
 #define WF_WARPS 32
