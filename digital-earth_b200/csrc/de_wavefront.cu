@@ -1,6 +1,6 @@
 // de_wavefront.cu -- the product integrator: persistent-thread, stage-sorted wavefront.
 //
-// Why: ncu on the one-thread-per-pixel kernel (profiles/r1_megakernel.md) shows 4.9 of 32 lanes
+// Why: ncu on the one-thread-per-pixel kernel (profiles/r1_wavefront.md) shows 4.9 of 32 lanes
 // active per issued instruction -- path length and stage mix diverge, memory does not matter
 // (L1 97 %, L2 98 % hits, DRAM idle).  This kernel keeps every lane of a warp inside the SAME
 // inner loop:
