@@ -11,7 +11,7 @@
  *
  * Pinning: Taichi itself is absent from this environment, so the reference
  * cannot be executed through its real compiler ("parity unpinned" at the
- * Taichi-runtime boundary).  What IS pinned: tests/golden/*.npz hold outputs
+ * Taichi-runtime boundary).  What IS pinned: tests/golden/ (.npz files) hold outputs
  * of the reference's own unmodified source files executed through the Taichi
  * stand-in in oracle/ti_shim (scalar f32, glibc libm); tests/test_oracle_golden.py
  * requires this file to reproduce them bit for bit, plus the known-answer
