@@ -320,6 +320,21 @@ DE_DEV float2 rsi(float3 pos, float3 dir, float r) {
 }
 
 #if !DE_EXACT
+// Product flavour: density bound AND interval of one cloud tracking pass over [ts, tm] (0 = nothing to track).
+// Where the texture is <= cmax the cloud layer ends at height 0.2 + 0.8 cmax of the shell (pathtracer.py:63: the density is
+// zero unless hgt - 0.2 < 0.8 c), so the part of the pass above that sphere could only produce null collisions: cutting it
+// leaves the distribution of real collisions unchanged and removes more than half of the cloud steps
+// (profiles/r1_bench.md).  The 1e-3 (6 m) margin covers rounding of hgt; a ray that misses the sphere yields rsi's NaN pair.
+DE_DEV float cloud_pass_setup(const DevScene &s, float3 o, float3 d, float &ts, float &tm) {
+    const float cmax = cloud_segment_cmax(s, o, d, ts, tm);
+    float bound = cloud_density_bound(cmax);
+    if (bound > 0.0f && cmax < 0.99f) {
+        const float2 top = rsi(o, d, kCloudsLower + kCloudsThickness * (0.2f + 0.8f * cmax + 1e-3f));
+        ts = fmaxf(ts, top.x); tm = fminf(tm, top.y);
+        if (!(top.y >= 0.0f && ts < tm)) bound = 0.0f;
+    }
+    return bound;
+}
 // Exact miss test for intersect_land (pathtracer.py:27-46), product flavour.  From the marching start
 // point p (distance s0 already travelled) the terrain SDF is >= alt - scale (heightmap <= 1).  The loop
 // only stops early when |dist| < 1e-4 * ray_dist.  If the lowest altitude the ray can still reach

@@ -160,8 +160,8 @@ DE_DEV int sample_interaction(const DevScene &s, float3 pos, float3 dir, float l
     if (rmo_event == kNullEvent || rmo_t > t_start) {
         float cloud_t; int cloud_id;
 #if !DE_EXACT
-        if (t_start < t_max) {  // product flavour: local majorant from the coarse cloud max-map (unbiased: any bound works)
-            float bound = cloud_density_bound(cloud_segment_cmax(s, pos, dir, t_start, t_max));
+        if (t_start < t_max) {  // product flavour: local majorant + layer top from the coarse cloud max-map (unbiased: any bound works)
+            float bound = cloud_pass_setup(s, pos, dir, t_start, t_max);
             if (bound == 0.0f) t_max = t_start; else max_cloud = ext_cloud * bound;
         }
 #endif
@@ -185,7 +185,7 @@ DE_DEV float sample_transmittance(const DevScene &s, float3 pos, float3 dir, flo
     intersect_cloud_limits(pos, dir, land_isection, t_start, t_max);
 #if !DE_EXACT
     if (t_start < t_max) {
-        float bound = cloud_density_bound(cloud_segment_cmax(s, pos, dir, t_start, t_max));
+        float bound = cloud_pass_setup(s, pos, dir, t_start, t_max);
         if (bound == 0.0f) t_max = t_start; else max_cloud = ext_cloud * bound;
     }
 #endif

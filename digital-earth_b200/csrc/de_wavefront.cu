@@ -393,7 +393,7 @@ DE_DEV uint32_t stage_rmo_done(Ctx &c, int slot) {
     bool enter = ts < tm;
     if (!ratio) enter = enter && (rmo_ev == kNullEvent || rmo_t > ts);
     if (enter) {
-        float bound = cloud_density_bound(cloud_segment_cmax(c.s, o, d, ts, tm));
+        const float bound = cloud_pass_setup(c.s, o, d, ts, tm);  // local majorant; the pass ends at the top of the local cloud layer
         if (bound > 0.0f) {
             c.pool.t[slot] = ts; c.pool.tmax[slot] = tm; c.pool.cmj[slot] = bound;
             return PK_SET_STAGE(pk, ST_CLOUD);  // PK_RATIO stays as it is
