@@ -216,3 +216,24 @@ def test_oracle_event_fixture_feeds_the_roofline_model():
     assert bench.oracle_events(A)["paths"] > 0
     A.tex = "123x45"
     assert bench.oracle_events(A) is None
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours) on a tiny sample: one JSON line with the contract keys."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--tex", "256x128",
+                          "--cpu-res", "96x64", "--cpu-spp", "1"], capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "0"})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
+    # ranks other than 0 of a torchrun launch print nothing and exit 0
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True, timeout=60,
+                         env={**os.environ, "RANK": "1"})
+    assert out.returncode == 0 and out.stdout.strip() == ""
