@@ -1,0 +1,194 @@
+"""The product flavour removes work with bounds it claims are EXACT: a local cloud majorant from a
+coarse dilated max-map, the top of the local cloud layer, an altitude-aware rmo majorant, a terrain miss test.  Unbiased
+tracking needs every one of them to hold at every point, not on average -- Monte Carlo tests cannot see a bound that fails
+on one ray in a million.  Here the bounds are restated in numpy exactly as csrc/de_device.cuh computes them and checked
+against the ORACLE's density / texture / terrain functions on dense samples of random rays (no GPU)."""
+import numpy as np
+import pytest
+
+import digital_earth_b200 as de
+from oracle import oracle as orc
+
+R, LOWER, UPPER, THICK, ATM = 6371000.0, 6375000.0, 6381000.0, 6000.0, 6481000.0
+F = np.float32
+
+
+def unit(rng, n):
+    d = rng.normal(size=(n, 3))
+    return (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(F)
+
+
+# ---- numpy restatements of the device helpers (float32 throughout, same expression order) --------------------------------
+def build_cloud_max(tex, b):
+    """k_build_cloud_max: cell = max over its b x b texels dilated by one texel (clamped at the borders)."""
+    h, w = tex.shape
+    cw, ch = (w + b - 1) // b, (h + b - 1) // b
+    out = np.zeros((ch, cw), np.uint8)
+    for cy in range(ch):
+        y0, y1 = max(cy * b - 1, 0), min(cy * b + b, h - 1)
+        for cx in range(cw):
+            x0, x1 = max(cx * b - 1, 0), min(cx * b + b, w - 1)
+            out[cy, cx] = tex[y0:y1 + 1, x0:x1 + 1].max()
+    return out
+
+
+def sphere_uv(p):
+    n = p / np.linalg.norm(p, axis=-1, keepdims=True)
+    u = (np.arctan2(n[..., 2], -n[..., 0]) / np.pi + 1.0) / 2.0
+    v = np.arcsin(np.clip(n[..., 1], -1, 1)) / np.pi + 0.5
+    return u - np.floor(u), v - np.floor(v)
+
+
+def cloud_segment_cmax(cm, b, tw, th, o, d, ts, tm):
+    """cloud_segment_cmax for ONE ray: bound of the texture over the great-circle footprint of [ts, tm], 1.0 = no information."""
+    theta = (tm - ts) / 6375000.0
+    if not theta < 0.25:
+        return 1.0
+    ua, va = sphere_uv(o + d * ts)
+    ub, vb = sphere_uv(o + d * tm)
+    if abs(ua - ub) > 0.4:
+        return 1.0
+    pad = theta * (0.5 / np.pi) + 1e-4      # (very conservative: the true excursion is ~ tan(lat) * theta^2 / 8; the one-texel dilation alone covers it below 4k maps)
+    vlo, vhi = min(va, vb) - pad, max(va, vb) + pad
+    if vlo < 0.05 or vhi > 0.95:
+        return 1.0
+    sx, sy = tw / b, th / b
+    ch, cw = cm.shape
+    cu0, cu1 = max(int((min(ua, ub) - 1e-4) * sx), 0), min(int((max(ua, ub) + 1e-4) * sx), cw - 1)
+    cv0, cv1 = max(int(vlo * sy), 0), min(int(vhi * sy), ch - 1)
+    if (cu1 - cu0 + 1) * (cv1 - cv0 + 1) > 48:
+        return 1.0
+    return float(cm[cv0:cv1 + 1, cu0:cu1 + 1].max()) / 255.0
+
+
+def rsi(o, d, r):
+    b = float(np.dot(o, d))
+    disc = b * b - float(np.dot(o, o)) + r * r
+    if disc < 0:
+        return None
+    s = np.sqrt(disc)
+    return -b - s, -b + s
+
+
+def cloud_limits(o, d, land):
+    return orc.cloud_limits(o[None].astype(F), d[None].astype(F), np.array([land], F))[0]
+
+
+@pytest.fixture(scope="module")
+def cloud_scene():
+    tex = de.textures.synthetic(2048, 1024, cloud_cover=0.5, seed=4)   # fine enough for a footprint's bulge to exceed the one-texel dilation
+    b = 8                                                   # de_upload_texture: max(w / 256, 8)
+    return tex, orc.Scene(tex, 64, 32), build_cloud_max(tex["clouds"], b), b
+
+
+def rays_through_the_shell(rng, n):
+    """origins from below the shell to far above it, directions biased towards the shell"""
+    o = unit(rng, n).astype(np.float64) * (R + rng.choice([50.0, 2000.0, 5000.0, 8000.0, 30000.0, 4e5, 1.3e6], n) * (0.5 + rng.random(n)))[:, None]
+    d = unit(rng, n).astype(np.float64)
+    down = rng.random(n) < 0.6
+    d[down] = -o[down] / np.linalg.norm(o[down], axis=1, keepdims=True) + 1.5 * unit(rng, int(down.sum()))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    # a third of the rays skim the shell almost horizontally at mid / high latitudes: passes up to 1600 km long, whose great-circle
+    # footprint bulges out of the latitude range of its end points (what the theta / 2 padding of the box is for)
+    k = n // 3
+    lat = np.radians(rng.uniform(25.0, 70.0, k)) * rng.choice([-1.0, 1.0], k)
+    lon = rng.uniform(-np.pi, np.pi, k)
+    up = np.stack([np.cos(lat) * np.cos(lon), np.sin(lat), np.cos(lat) * np.sin(lon)], axis=1)
+    east = np.stack([-np.sin(lon), np.zeros(k), np.cos(lon)], axis=1)
+    d[:k] = east * rng.choice([-1.0, 1.0], k)[:, None]
+    # the ray's lowest (and most poleward) point lies INSIDE the pass: start up to 800 km before it
+    o[:k] = up * (R + rng.uniform(3500.0, 10500.0, k))[:, None] - d[:k] * rng.uniform(0.0, 8.0e5, k)[:, None]
+    return o, d
+
+
+def test_cloud_majorant_and_layer_top_are_exact_bounds(cloud_scene):
+    tex, scene, cm, b = cloud_scene
+    th, tw = tex["clouds"].shape
+    rng = np.random.default_rng(11)
+    o, d = rays_through_the_shell(rng, 6000)
+    informative = cut = checked = 0
+    for i in range(len(o)):
+        ts, tm = (float(x) for x in cloud_limits(o[i], d[i], -1.0))
+        if not ts < tm:
+            continue
+        cmax = cloud_segment_cmax(cm, b, tw, th, o[i], d[i], ts, tm)
+        t = ts + (tm - ts) * np.linspace(0.0, 1.0, 97)
+        pts = (o[i] + d[i] * t[:, None]).astype(F)
+        c = orc.tex_fetch(tex["clouds"], pts)[:, 0]
+        dens = orc.clouds_density(scene, pts)
+        checked += 1
+        if cmax < 1.0:
+            informative += 1
+            assert c.max() <= cmax + 1e-6, (i, c.max(), cmax)                       # the max-map bounds the bilinear texture
+        assert dens.max() <= max(cmax, 0.4) * 0.029 * (1 + 1e-6) + (0.0 if cmax > 0 else 0.0)   # cloud_density_bound
+        if cmax == 0.0:
+            assert dens.max() == 0.0                                                 # the pass is skipped
+        elif cmax < 0.99:                                                            # cloud_pass_setup: cut at the layer top
+            top = rsi(o[i], d[i], LOWER + THICK * (0.2 + 0.8 * cmax + 1e-3))
+            ts2, tm2 = (ts, ts) if top is None else (max(ts, top[0]), min(tm, top[1]))
+            outside = (t < ts2) | (t > tm2)
+            cut += int(outside.any())
+            assert dens[outside].max(initial=0.0) == 0.0, (i, cmax)                   # nothing but null collisions was removed
+    assert checked > 2000 and informative > 0.5 * checked and cut > 0.2 * checked, (checked, informative, cut)
+
+
+def test_rmo_majorant_bounds_every_point_of_the_segment():
+    rng = np.random.default_rng(12)
+    n = 4000
+    o = unit(rng, n).astype(np.float64) * (R + rng.random(n) ** 2 * 130e3)[:, None]
+    d = unit(rng, n).astype(np.float64)
+    wl = rng.integers(0, 256, n)
+    ext_all = orc.spectra(np.array([390.0 + 441.0 * (2 * k + 1) / 512.0 for k in range(256)], F))[:, :3].astype(np.float64)
+    bad = 0
+    for i in range(n):
+        hit = rsi(o[i], d[i], ATM)
+        if hit is None or hit[1] <= 0:
+            continue
+        ts, tm = max(0.0, hit[0]), hit[1]
+        land = rsi(o[i], d[i], R)
+        if land is not None and land[0] > ts:
+            tm = min(tm, land[0])
+        if not ts < tm:
+            continue
+        # rmo_segment_majorant: densities at the LOWEST point of the segment (perigee clamped to it)
+        bdot, r2 = float(np.dot(o[i], d[i])), float(np.dot(o[i], o[i]))
+        tp = min(max(-bdot, ts), tm)
+        hmin = max(np.sqrt(max(r2 + tp * (2 * bdot + tp), 0.0)) - R - 2.0, 0.0)
+        dl = orc.density(np.array([hmin], F))[0].astype(np.float64)
+        oz = 1.0 if hmin < 25000.0 else dl[2]
+        ext = ext_all[wl[i]]
+        maj = 1.001 * (ext[0] * dl[0] + ext[1] * dl[1]) + ext[2] * oz
+        t = ts + (tm - ts) * np.linspace(0.0, 1.0, 129)
+        h = np.linalg.norm(o[i] + d[i] * t[:, None], axis=1) - R
+        dens = orc.density(h.astype(F)).astype(np.float64)
+        sig = dens @ ext
+        bad += int(sig.max() > maj * (1 + 2e-6))
+    assert bad == 0
+
+
+def test_land_surely_missed_never_discards_a_hit():
+    tex = de.textures.synthetic(256, 128, seed=6)
+    scene = orc.Scene(tex, 64, 32)
+    scale = 7800.0
+    rng = np.random.default_rng(13)
+    n = 20000
+    o = unit(rng, n).astype(np.float64) * (R + 10.0 + rng.random(n) ** 3 * 3.0e6)[:, None]
+    d = unit(rng, n).astype(np.float64)
+    graze = rng.random(n) < 0.5                              # half of the rays skim the terrain shell
+    t_dir = np.cross(o[graze], unit(rng, int(graze.sum())))
+    t_dir /= np.linalg.norm(t_dir, axis=1, keepdims=True)
+    d[graze] = t_dir + (rng.random((int(graze.sum()), 1)) - 0.6) * 0.2 * o[graze] / np.linalg.norm(o[graze], axis=1, keepdims=True)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    hit = orc.intersect_land(scene, o.astype(F), d.astype(F))
+    # setup_sdf: the march starts where the ray enters the atmosphere (or at the origin), land_surely_missed is evaluated there
+    flagged = np.zeros(n, bool)
+    for i in range(n):
+        a = rsi(o[i], d[i], ATM)
+        s0 = a[0] if (a is not None and a[0] > 0) else 0.0
+        p = o[i] + d[i] * s0
+        b, r2 = float(np.dot(p, d[i])), float(np.dot(p, p))
+        rmin2 = r2 if b >= 0 else r2 - b * b
+        need = R + scale + 1e-4 * (s0 + max(-b, 0.0)) + 100.0
+        flagged[i] = rmin2 > need * need
+    assert flagged.sum() > 0.2 * n and (~flagged).sum() > 0.2 * n
+    assert (hit[flagged] < 0).all(), "the miss test discarded a ray the reference's march hits"
