@@ -277,7 +277,7 @@ DE_DEV float3 sample_sphere_rgb8(const DevTex &t, float3 pos) { float2 uv = sphe
 #if !DE_EXACT
 // Upper bound of the cloud texture along the part [ts, tm] of a ray (product flavour).
 // A straight ray projects onto a great-circle arc: longitude is monotone along it (arcs shorter than
-// pi that stay away from the poles), latitude leaves the endpoint range by at most theta/2.  The
+// pi that stay away from the poles), latitude leaves the endpoint range by at most ~theta^2/8 * tan(lat).  The
 // bound is the maximum of the dilated coarse map over that lat-long box; 1.0 (no information)
 // whenever the box is unsafe (date-line crossing, polar caps, long arcs, too many cells).
 DE_DEV float cloud_segment_cmax(const DevScene &s, float3 o, float3 d, float ts, float tm) {
@@ -286,9 +286,13 @@ DE_DEV float cloud_segment_cmax(const DevScene &s, float3 o, float3 d, float ts,
     if (!(theta < 0.25f)) return 1.0f;
     float2 a = sphere_uv(o + d * ts), b = sphere_uv(o + d * tm);
     if (fabsf(a.x - b.x) > 0.4f) return 1.0f;
-    float pad = theta * (0.5f / kPi) + 1e-4f;
+    // latitude: sin(lat) is a sinusoid of amplitude <= 1 along the arc, so it leaves the end points' range by at most
+    // 1 - cos(theta/2) <= theta^2/8; inside |lat| <= 81 deg (which the coarse test with the trivial bound theta/2 guarantees)
+    // d(v)/d(sin lat) <= 1/(pi cos 81deg), hence 0.2544 theta^2 in v.  (The trivial bound alone made the box 10-60x too tall.)
+    const float pad_coarse = theta * (0.5f / kPi) + 1e-4f;
+    if (fminf(a.y, b.y) - pad_coarse < 0.05f || fmaxf(a.y, b.y) + pad_coarse > 0.95f) return 1.0f;
+    const float pad = 0.2544f * theta * theta + 1e-4f;
     float vlo = fminf(a.y, b.y) - pad, vhi = fmaxf(a.y, b.y) + pad;
-    if (vlo < 0.05f || vhi > 0.95f) return 1.0f;
     float sx = (float)s.tex[3].w / (float)s.cm_b, sy = (float)s.tex[3].h / (float)s.cm_b;
     int cu0 = max((int)((fminf(a.x, b.x) - 1e-4f) * sx), 0), cu1 = min((int)((fmaxf(a.x, b.x) + 1e-4f) * sx), s.cm_w - 1);
     int cv0 = max((int)(vlo * sy), 0), cv1 = min((int)(vhi * sy), s.cm_h - 1);

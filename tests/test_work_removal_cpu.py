@@ -48,10 +48,11 @@ def cloud_segment_cmax(cm, b, tw, th, o, d, ts, tm):
     ub, vb = sphere_uv(o + d * tm)
     if abs(ua - ub) > 0.4:
         return 1.0
-    pad = theta * (0.5 / np.pi) + 1e-4      # (very conservative: the true excursion is ~ tan(lat) * theta^2 / 8; the one-texel dilation alone covers it below 4k maps)
-    vlo, vhi = min(va, vb) - pad, max(va, vb) + pad
-    if vlo < 0.05 or vhi > 0.95:
+    pad_coarse = theta * (0.5 / np.pi) + 1e-4               # trivial bound theta / 2: keeps the whole arc inside |lat| <= 81 deg
+    if min(va, vb) - pad_coarse < 0.05 or max(va, vb) + pad_coarse > 0.95:
         return 1.0
+    pad = 0.2544 * theta * theta + 1e-4                     # 1 - cos(theta / 2) in sin(lat), through d v / d sin(lat) <= 1 / (pi cos 81 deg)
+    vlo, vhi = min(va, vb) - pad, max(va, vb) + pad
     sx, sy = tw / b, th / b
     ch, cw = cm.shape
     cu0, cu1 = max(int((min(ua, ub) - 1e-4) * sx), 0), min(int((max(ua, ub) + 1e-4) * sx), cw - 1)
