@@ -344,8 +344,12 @@ DE_DEV float cloud_pass_setup(const DevScene &s, float3 o, float3 d, float &ts, 
 // only stops early when |dist| < 1e-4 * ray_dist.  If the lowest altitude the ray can still reach
 // (perigee if it is approaching, the start point if it is receding) clears the tallest terrain by more
 // than 1e-4 * (distance travelled until then) -- afterwards altitude grows like x^2/2r, which beats
-// 1e-4 x by construction -- every iterate keeps dist > threshold, ray_dist runs past 10 R and the
-// reference returns -1.  100 m of slack covers f32 cancellation for cameras at 5.7e7 m.
+// 1e-4 x by construction -- every iterate keeps dist > threshold, so the reference's stopping test can
+// never fire: its loop runs ray_dist past 10 R and returns -1.  100 m of slack covers f32 cancellation
+// for cameras at 5.7e7 m.  One caveat, a deviation on purpose: a ray that skims the
+// tallest terrain so closely that the reference's march is still crawling after its 250 iterations is
+// returned by the reference as a "hit" at wherever it got to (pathtracer.py:37,46); here it is a miss.
+// Measured frequency: 2.5e-6 of isotropic rays started 0.1-12 km above the ground.
 DE_DEV bool land_surely_missed(float3 p, float3 dir, float s0, float scale) {
     float b = dot(p, dir), r2 = dot(p, p);
     float rmin2 = b >= 0.0f ? r2 : r2 - b * b;
@@ -353,8 +357,8 @@ DE_DEV bool land_surely_missed(float3 p, float3 dir, float s0, float scale) {
     return rmin2 > need * need;
 }
 // Same argument at an iterate of the march (s = distance travelled so far): above every terrain by more
-// than the stopping tolerance can still reach, and receding => the reference's loop can only run off to
-// 10 R and return -1.
+// than the stopping tolerance can still reach, and receding => the reference's stopping test cannot fire
+// any more (same iteration-cap caveat as above).
 DE_DEV bool march_surely_missed(float3 ro, float3 dir, float r2, float s, float scale) {
     float need = kPlanetR + scale + 1e-4f * s + 100.0f;
     return r2 > need * need && dot(ro, dir) > 0.0f;

@@ -221,3 +221,43 @@ def test_fitted_atan2_and_asin_meet_their_stated_accuracy():
     assert np.abs(rr.astype(np.float64) - np.arcsin(z.astype(np.float64))).max() < 3e-7
     # in texels of the widest map the reference ships (21600): far below the filter's own resolution
     assert 6e-7 / (2 * np.pi) * 21600 < 0.0025
+
+
+def test_march_surely_missed_only_fires_on_marches_that_end_in_a_miss():
+    """The in-loop exit of the terrain march (march_surely_missed): at an iterate that is above every possible terrain by more than the
+    stopping tolerance can still reach AND receding, no later iterate can satisfy the reference's stopping test (pathtracer.py:43), so its
+    loop can only run off to 10 R -- or run out of its 250 iterations, in which case the reference returns the distance it has crawled
+    to as if it were a hit (pathtracer.py:37,46).  The march is replayed in numpy on the oracle's height fetch: wherever the exit would
+    fire, the oracle's own intersect_land must say -1 unless the replay ended by that iteration cap (DESIGN.md section 8 lists the
+    deviation; skimming rays like these are a 1e-5 fraction of the marches of a frame)."""
+    tex = de.textures.synthetic(256, 128, seed=6)
+    scene = orc.Scene(tex, 64, 32)
+    scale = 7800.0
+    rng = np.random.default_rng(15)
+    n = 3000
+    up = unit(rng, n).astype(np.float64)
+    o = up * (R + rng.uniform(200.0, 60000.0, n))[:, None]
+    tang = np.cross(up, unit(rng, n)); tang /= np.linalg.norm(tang, axis=1, keepdims=True)
+    d = tang + up * rng.uniform(-0.2, 0.05, n)[:, None]       # skimming rays: the ones that pass close over mountains and leave again
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    truth = orc.intersect_land(scene, o.astype(F), d.astype(F))
+    fired = np.zeros(n, bool)
+    t = np.zeros(n)
+    a = np.array([rsi(o[i], d[i], ATM) or (0.0, 0.0) for i in range(n)])
+    t[:] = np.where(a[:, 0] > 0, a[:, 0], 0.0)
+    alive = np.ones(n, bool)
+    for it in range(250):
+        ro = o + d * t[:, None]
+        r2 = np.einsum("ij,ij->i", ro, ro)
+        need = R + scale + 1e-4 * t + 100.0
+        fired |= alive & (r2 > need * need) & (np.einsum("ij,ij->i", ro, d) > 0)
+        hgt = orc.tex_fetch(tex["topography"], ro.astype(F))[:, 0].astype(np.float64)
+        dist = np.sqrt(r2) - R - scale * hgt
+        t = np.where(alive, t + dist, t)
+        alive &= ~((t > 63710000.0) | (np.abs(dist) < t * 1e-4))
+        if not alive.any():
+            break
+    capped = alive                                           # still marching after 250 iterations: the reference reports t as a hit
+    assert fired.sum() > 0.2 * n and (truth > 0).sum() > 0.1 * n, (fired.sum(), (truth > 0).sum())
+    assert (truth[fired & ~capped] < 0).all(), "the early exit fired on a march the reference finishes with a converged hit"
+    assert (fired & capped & (truth > 0)).sum() < 0.02 * n  # the iteration-cap artefact, even in this family of skimming rays
