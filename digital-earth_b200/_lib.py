@@ -42,6 +42,9 @@ _SIGS = {
     "de_last_error": ([_P], C.c_char_p),
     "de_set_stream": ([_P, _P], _I),
     "de_set_mode": ([_P, _I], _I),
+    "de_set_option": ([_P, C.c_char_p, _I], _I),
+    "de_get_moment2": ([_P, C.POINTER(_P)], _I),
+    "de_get_launch_timeline": ([_P, _P], _I),
     "de_set_params": ([_P, C.POINTER(DeParams)], _I),
     "de_upload_texture": ([_P, _I, _P, _I, _I, _I], _I),
     "de_upload_luts": ([_P, _P, _P, _P, _P, _I], _I),
@@ -84,6 +87,9 @@ _SIGS = {
     "de_test_trace_paths": ([_P, _P, _P, _P, _U, _P, _I], _I),
     "de_test_trace_preview": ([_P, _P, _P, _P, _U, _P, _I], _I),
     "de_test_ray_march": ([_P, _P, _P, _P, _P, _P, _P, _P, _I], _I),
+    "de_test_fast_cloud_bound": ([_P, _P, _P, _P, _P, _P, _I], _I),
+    "de_test_fast_rmo_majorant": ([_P, _P, _P, _P, _P, _P, _P, _I], _I),
+    "de_test_fast_land": ([_P, _P, _P, _P, _I], _I),
 }
 EXPORTS = tuple(_SIGS)
 

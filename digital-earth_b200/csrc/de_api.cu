@@ -26,6 +26,9 @@ struct de_ctx {
     LambdaRow *d_lam = nullptr;
     DevDerived *d_derived = nullptr;
     float *d_accum = nullptr, *d_image = nullptr;
+    float *d_accum2 = nullptr;                     // optional per-pixel second moments (de_set_option "moments")
+    bool opt_space_tiles = true, opt_space_async = true, opt_timeline = false;
+    unsigned long long param_version = 1;          // bumps with every de_set_params (tile classification cache key)
     uint8_t *d_cloud_max = nullptr;
     unsigned long long *d_counters = nullptr;
     DeWavefrontState *wf = nullptr;
@@ -83,8 +86,11 @@ int refresh_scene(de_ctx *ctx) {
 int ready_to_render(de_ctx *ctx) {
     if (!ctx->have_params) return fail(ctx, DE_ERR_STATE, "de_set_params has not been called");
     if (!ctx->have_luts) return fail(ctx, DE_ERR_STATE, "de_upload_luts has not been called");
-    for (int i = 0; i < DE_TEX_COUNT; ++i)
+    for (int i = 0; i < DE_TEX_COUNT; ++i) {
         if (!ctx->have_tex[i]) return fail(ctx, DE_ERR_STATE, "texture slot " + std::to_string(i) + " has not been uploaded");
+        if (ctx->mode == DE_MODE_PARITY && !ctx->scene.tex[i].data)
+            return fail(ctx, DE_ERR_STATE, "the parity flavour reads the row-major texture copies, which were released (option linear_textures)");
+    }
     return refresh_scene(ctx);
 }
 }  // namespace
@@ -129,7 +135,7 @@ void de_destroy(de_ctx *ctx) {
     for (void *p : ctx->ipc_open) cudaIpcCloseMemHandle(p);
     cudaFree(ctx->d_cie); cudaFree(ctx->d_s2s); cudaFree(ctx->d_o3); cudaFree(ctx->d_crf); cudaFree(ctx->d_cdf);
     cudaFree(ctx->d_cloud_max);
-    cudaFree(ctx->d_lam); cudaFree(ctx->d_derived); cudaFree(ctx->d_accum); cudaFree(ctx->d_image); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_lam); cudaFree(ctx->d_derived); cudaFree(ctx->d_accum); cudaFree(ctx->d_accum2); cudaFree(ctx->d_image); cudaFree(ctx->d_counters);
     delete ctx;
 }
 
@@ -137,7 +143,61 @@ const char *de_last_error(de_ctx *ctx) { return ctx ? ctx->err.c_str() : "null c
 
 int de_set_stream(de_ctx *ctx, void *cuda_stream) {
     ENTER();
-    ctx->stream = (cudaStream_t)cuda_stream;
+    cudaStream_t ns = (cudaStream_t)cuda_stream;
+    if (ns != ctx->stream) {  // work already queued on the old stream (render, k_prepare) is ordered before anything on the new one
+        cudaEvent_t ev;
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e1 = cudaEventRecord(ev, ctx->stream), e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(ns, ev, 0) : e1;
+        cudaEventDestroy(ev);
+        if (e2 != cudaSuccess) return fail(ctx, DE_ERR_CUDA, std::string("de_set_stream: ") + cudaGetErrorString(e2));
+        ctx->stream = ns;
+    }
+    return DE_OK;
+}
+int de_set_option(de_ctx *ctx, const char *name, int value) {
+    ENTER();
+    NEED(name, "name is NULL");
+    const std::string n(name);
+    if (n == "space_tiles") ctx->opt_space_tiles = value != 0;
+    else if (n == "space_async") ctx->opt_space_async = value != 0;
+    else if (n == "timeline") ctx->opt_timeline = value != 0;
+    else if (n == "linear_textures") {
+        // The row-major copies of the maps are read by the parity flavour and the test hooks only; the product integrators
+        // sample the block-linear arrays.  0 frees them (2.3 GB at the NASA resolution); they come back with the next upload.
+        NEED(value == 0, "linear_textures can only be released (0); upload the textures again to restore them");
+        CU(cudaDeviceSynchronize());
+        for (int i = 0; i < DE_TEX_COUNT; ++i) { cudaFree(ctx->d_tex[i]); ctx->d_tex[i] = nullptr; ctx->scene.tex[i].data = nullptr; }
+    }
+    else if (n == "moments") {
+        if (value && !ctx->d_accum2) {
+            size_t bytes = (size_t)ctx->W * ctx->H * 3 * sizeof(float);
+            CU(cudaMalloc(&ctx->d_accum2, bytes));
+            CU(cudaMemsetAsync(ctx->d_accum2, 0, bytes, ctx->stream));
+        } else if (!value && ctx->d_accum2) {
+            CU(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_accum2); ctx->d_accum2 = nullptr;
+        }
+    } else return fail(ctx, DE_ERR_INVALID, "unknown option '" + n + "'");
+    return DE_OK;
+}
+int de_get_moment2(de_ctx *ctx, float **dev_ptr) {
+    ENTER();
+    NEED(dev_ptr, "dev_ptr is NULL");
+    if (!ctx->d_accum2) return fail(ctx, DE_ERR_STATE, "second moments are off: de_set_option(ctx, \"moments\", 1) first");
+    *dev_ptr = ctx->d_accum2;
+    return DE_OK;
+}
+int de_get_launch_timeline(de_ctx *ctx, uint64_t *out8) {
+    ENTER();
+    NEED(out8, "out is NULL");
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->wf) return fail(ctx, DE_ERR_STATE, "the wavefront integrator has not run yet");
+    unsigned long long buf[40];
+    if (de_wavefront_profile(ctx->wf, buf) != 0) return fail(ctx, DE_ERR_CUDA, "timeline copy failed");
+    for (int k = 0; k < 7; ++k) out8[k] = buf[32 + k];
+    unsigned int tc[2] = {0u, 0u};
+    de_wavefront_tile_counts(ctx->wf, tc);
+    out8[7] = ((uint64_t)tc[1] << 32) | tc[0];
     return DE_OK;
 }
 int de_set_mode(de_ctx *ctx, int mode) {
@@ -151,7 +211,10 @@ int de_get_stage_profile(de_ctx *ctx, uint64_t *out32) {
     NEED(out32, "out is NULL");
     CU(cudaStreamSynchronize(ctx->stream));
     if (!ctx->wf) return fail(ctx, DE_ERR_STATE, "the wavefront integrator has not run yet");
-    return de_wavefront_profile(ctx->wf, (unsigned long long *)out32) == 0 ? DE_OK : fail(ctx, DE_ERR_CUDA, "profile copy failed");
+    unsigned long long buf[40];
+    if (de_wavefront_profile(ctx->wf, buf) != 0) return fail(ctx, DE_ERR_CUDA, "profile copy failed");
+    for (int k = 0; k < 32; ++k) out32[k] = buf[k];
+    return DE_OK;
 }
 int de_set_counting(de_ctx *ctx, int enabled) {
     ENTER();
@@ -166,6 +229,7 @@ int de_set_params(de_ctx *ctx, const DeParams *p) {
     ctx->params = *p;
     ctx->have_params = true;
     ctx->derived_dirty = true;
+    ++ctx->param_version;
     return DE_OK;
 }
 
@@ -177,9 +241,14 @@ int de_upload_texture(de_ctx *ctx, int slot, const uint8_t *host, int w, int h, 
     NEED(channels == (rgb ? 3 : 1), "albedo/stars take 3 channels, the other maps 1");
     size_t bytes = (size_t)w * h * channels;
     DevTex &t = ctx->scene.tex[slot];
+    CU(cudaStreamSynchronize(ctx->stream));  // a render in flight may still sample the old texture (destroying an object does not synchronise)
+    if (ctx->wf) CU(cudaDeviceSynchronize());
+    ctx->have_tex[slot] = false;             // the slot is empty until the new map is completely in place
     if (t.obj) { cudaDestroyTextureObject(t.obj); t.obj = 0; }
     if (ctx->arr[slot]) { cudaFreeArray(ctx->arr[slot]); ctx->arr[slot] = nullptr; }
     cudaFree(ctx->d_tex[slot]); ctx->d_tex[slot] = nullptr;
+    t.data = nullptr; t.w = t.h = t.c = 0;
+    if (slot == DE_TEX_CLOUDS) { ctx->scene.cloud_max = nullptr; }
     CU(cudaMalloc(&ctx->d_tex[slot], bytes));
     CU(cudaMemcpyAsync(ctx->d_tex[slot], host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     // block-linear copy behind a point-sampled, clamped, unnormalised-coordinate texture object:
@@ -247,6 +316,7 @@ int de_reset(de_ctx *ctx) {
     ENTER();
     CU(cudaMemsetAsync(ctx->d_accum, 0, (size_t)ctx->W * ctx->H * 3 * sizeof(float), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeCounters), ctx->stream));
+    if (ctx->d_accum2) CU(cudaMemsetAsync(ctx->d_accum2, 0, (size_t)ctx->W * ctx->H * 3 * sizeof(float), ctx->stream));
     return DE_OK;
 }
 
@@ -256,15 +326,22 @@ int de_accumulate(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, 
     NEED(x0 >= 0 && y0 >= 0 && w > 0 && h > 0 && x0 + w <= ctx->W && y0 + h <= ctx->H, "window outside the frame");
     int rc = ready_to_render(ctx);
     if (rc) return rc;
-    if (ctx->mode == DE_MODE_PARITY) de_exact::launch_render_mega(ctx->scene, ctx->d_accum, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
-    else if (ctx->mode == DE_MODE_PREVIEW) de_fast::launch_render_preview(ctx->scene, ctx->d_accum, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
-    else if (ctx->mode == DE_MODE_MEGAKERNEL) de_fast::launch_render_mega(ctx->scene, ctx->d_accum, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
+    float *a2 = ctx->d_accum2;
+    if (ctx->mode == DE_MODE_PARITY) de_exact::launch_render_mega(ctx->scene, ctx->d_accum, a2, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
+    else if (ctx->mode == DE_MODE_PREVIEW) de_fast::launch_render_preview(ctx->scene, ctx->d_accum, a2, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
+    else if (ctx->mode == DE_MODE_MEGAKERNEL) de_fast::launch_render_mega(ctx->scene, ctx->d_accum, a2, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
     else {
         if (!ctx->wf) {
             ctx->wf = de_wavefront_alloc(ctx->device);
             if (!ctx->wf) return fail(ctx, DE_ERR_NOMEM, "wavefront state allocation failed");
         }
-        de_wavefront_render(ctx->wf, ctx->scene, ctx->d_accum, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
+        DeWavefrontJob job;
+        job.accum = ctx->d_accum; job.accum2 = a2; job.n_spp = n_spp; job.seed = seed; job.first_sample = first_sample;
+        job.x0 = x0; job.y0 = y0; job.w = w; job.h = h;
+        job.count = ctx->counting; job.timeline = ctx->opt_timeline;
+        job.space_tiles = ctx->opt_space_tiles; job.space_async = ctx->opt_space_async;
+        job.param_version = ctx->param_version;
+        if (de_wavefront_render(ctx->wf, ctx->scene, job, ctx->stream) != 0) return fail(ctx, DE_ERR_NOMEM, "wavefront tile buffers: allocation failed");
     }
     return check_launch(ctx, "render");
 }
@@ -284,8 +361,9 @@ int de_resolve(de_ctx *ctx, const float *accum_override, float *dev_out, int spp
     int rc = refresh_scene(ctx);
     if (rc) return rc;
     const float *src = accum_override ? accum_override : ctx->d_accum;
-    if (ctx->mode == DE_MODE_PARITY) de_exact::launch_resolve(ctx->scene, src, dev_out, spp_total, ctx->stream);
-    else de_fast::launch_resolve(ctx->scene, src, dev_out, spp_total, ctx->stream);
+    // _render_to_image always runs in IEEE source-order arithmetic (the 1e-5 tonemap gate of the north star holds for every
+    // mode): the kernel is 25 MB in / 25 MB out, fast intrinsics would buy nothing
+    de_exact::launch_resolve(ctx->scene, src, dev_out, spp_total, ctx->stream);
     return check_launch(ctx, "resolve");
 }
 
@@ -333,8 +411,7 @@ int de_resolve_peers(de_ctx *ctx, const float *const *peer_accums, int n_peers, 
     if (!ctx->have_params || !ctx->have_luts) return fail(ctx, DE_ERR_STATE, "params / LUTs missing");
     int rc = refresh_scene(ctx);
     if (rc) return rc;
-    if (ctx->mode == DE_MODE_PARITY) de_exact::launch_resolve_peers(ctx->scene, ctx->d_accum, peer_accums, n_peers, dev_out, spp_total, ctx->stream);
-    else de_fast::launch_resolve_peers(ctx->scene, ctx->d_accum, peer_accums, n_peers, dev_out, spp_total, ctx->stream);
+    de_exact::launch_resolve_peers(ctx->scene, ctx->d_accum, peer_accums, n_peers, dev_out, spp_total, ctx->stream);
     return check_launch(ctx, "resolve_peers");
 }
 
@@ -367,7 +444,10 @@ int de_get_counters(de_ctx *ctx, DeCounters *out) {
     ENTER();                                                                     \
     NEED(n >= 0, "n < 0");                                                       \
     if (n == 0) return DE_OK;                                                    \
-    if (needs_scene) { int rc_ = refresh_scene(ctx); if (rc_) return rc_; }
+    if (needs_scene) {                                                           \
+        int rc_ = refresh_scene(ctx); if (rc_) return rc_;                       \
+        for (int i_ = 0; i_ < DE_TEX_COUNT; ++i_) NEED(!ctx->have_tex[i_] || ctx->scene.tex[i_].data, "row-major texture copies were released (option linear_textures)"); \
+    }
 #define HOOK_POST(name) return check_launch(ctx, name)
 
 int de_test_philox(de_ctx *ctx, const uint32_t *in6, uint32_t *out4, int n) { HOOK_PRE(false); de_exact::t_philox(in6, out4, n, ctx->stream); HOOK_POST("philox"); }
@@ -407,6 +487,19 @@ int de_test_trace_preview(de_ctx *ctx, const int32_t *px, const int32_t *py, con
     if (rc) return rc;
     de_exact::t_trace_preview(ctx->scene, px, py, sample, seed, out, n, ctx->stream);
     HOOK_POST("trace_preview");
+}
+int de_test_fast_cloud_bound(de_ctx *ctx, const float *pos, const float *dir, const float *ts, const float *tm, float *out4, int n) {
+    HOOK_PRE(true);
+    NEED(ctx->have_tex[DE_TEX_CLOUDS], "cloud texture not uploaded");
+    de_fast::t_fast_cloud_bound(ctx->scene, pos, dir, ts, tm, out4, n, ctx->stream); HOOK_POST("fast_cloud_bound");
+}
+int de_test_fast_rmo_majorant(de_ctx *ctx, const float *pos, const float *dir, const float *ts, const float *tm, const float *ext3, float *out, int n) {
+    HOOK_PRE(false); de_fast::t_fast_rmo_majorant(pos, dir, ts, tm, ext3, out, n, ctx->stream); HOOK_POST("fast_rmo_majorant");
+}
+int de_test_fast_land(de_ctx *ctx, const float *pos, const float *dir, float *out3, int n) {
+    HOOK_PRE(true);
+    NEED(ctx->have_tex[DE_TEX_TOPOGRAPHY], "topography texture not uploaded");
+    de_fast::t_fast_land(ctx->scene, pos, dir, out3, n, ctx->stream); HOOK_POST("fast_land");
 }
 int de_test_trace_paths(de_ctx *ctx, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out, int n) {
     ENTER();

@@ -329,12 +329,19 @@ DE_DEV float2 rsi(float3 pos, float3 dir, float r) {
 // zero unless hgt - 0.2 < 0.8 c), so the part of the pass above that sphere could only produce null collisions: cutting it
 // leaves the distribution of real collisions unchanged and removes more than half of the cloud steps
 // (profiles/r1_bench.md).  The 1e-3 (6 m) margin covers rounding of hgt; a ray that misses the sphere yields rsi's NaN pair.
+// pos_noise: bound on |fl(o + d t) - (o + d t)| for t <= tm (two f32 roundings per component of magnitude <= |o| + t).
+DE_DEV float pos_noise(float3 o, float tm) { return 3e-7f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + tm); }
 DE_DEV float cloud_pass_setup(const DevScene &s, float3 o, float3 d, float &ts, float &tm) {
     const float cmax = cloud_segment_cmax(s, o, d, ts, tm);
     float bound = cloud_density_bound(cmax);
     if (bound > 0.0f && cmax < 0.99f) {
-        const float2 top = rsi(o, d, kCloudsLower + kCloudsThickness * (0.2f + 0.8f * cmax + 1e-3f));
-        ts = fmaxf(ts, top.x); tm = fminf(tm, top.y);
+        // The top sphere is intersected from the pass's entry point (|p| ~ 6.4e6 m): from a far camera (Apollo: |o| = 5.7e7 m,
+        // o.o ~ 3e15 with an ulp of 2.7e8) the discriminant of rsi(o, ...) is off by tens of metres of radius.  Tracked positions
+        // are o + d t in f32, i.e. up to pos_noise() away from the ideal ray, so the margin grows with the camera distance.
+        const float margin = 1e-3f + pos_noise(o, tm) * (1.0f / kCloudsThickness);
+        const float2 top = rsi(o + d * ts, d, kCloudsLower + kCloudsThickness * (0.2f + 0.8f * cmax + margin));
+        const float t0 = ts;
+        ts = fmaxf(ts, t0 + top.x); tm = fminf(tm, t0 + top.y);
         if (!(top.y >= 0.0f && ts < tm)) bound = 0.0f;
     }
     return bound;
@@ -413,9 +420,13 @@ DE_DEV float get_elevation(float3 p) { return sqrtf(p.x * p.x + p.y * p.y + p.z 
 // at the LOWEST point of the segment bound the whole segment.  The reference uses the sea-level values
 // everywhere (pathtracer.py:336,355); any valid majorant leaves delta / ratio tracking unbiased.
 DE_DEV float rmo_segment_majorant(float3 ext, float3 o, float3 d, float ts, float tm) {
-    float b = dot(o, d), r2 = dot(o, o);
-    float tp = fminf(fmaxf(-b, ts), tm);                    // perigee clamped to the segment
-    float hmin = fmaxf(sqrtf(fmaxf(r2 + tp * (2.0f * b + tp), 0.0f)) - kPlanetR - 2.0f, 0.0f);  // 2 m of f32 slack
+    // perigee from the segment's entry point p (|p| <= 6.5e6 m, r^2 resolves 0.3 m): evaluated from a far camera
+    // (|o| = 5.7e7 m) the cancellation in o.o + t (2 o.d + t) left hmin up to ~70 m too high
+    const float3 p = o + d * ts;
+    const float b = dot(p, d), r2 = dot(p, p);
+    const float tp = fminf(fmaxf(-b, 0.0f), tm - ts);       // perigee clamped to the segment
+    const float slack = 2.0f + pos_noise(o, tm);            // tracked positions are fl(o + d t): up to pos_noise() below the ideal ray
+    float hmin = fmaxf(sqrtf(fmaxf(r2 + tp * (2.0f * b + tp), 0.0f)) - kPlanetR - slack, 0.0f);
     float oz = hmin < 25000.0f ? 1.0f : get_ozone_density(hmin);
     return 1.001f * (ext.x * get_rayl_density(hmin) + ext.y * get_mie_density(hmin)) + ext.z * oz;
 }

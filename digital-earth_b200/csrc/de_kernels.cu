@@ -12,7 +12,7 @@ namespace DE_NS {
 // Renderer.render (renderer.py:283-330): one thread per pixel, a 16x8 film tile per 128-thread
 // CTA as in renderer.py:43-46,304; n_spp samples per launch instead of one.
 template <bool COUNT, bool PREVIEW>
-__global__ void __launch_bounds__(128) k_render_mega(DevScene s, float *__restrict__ accum, int n_spp, uint32_t seed, uint32_t first_sample,
+__global__ void __launch_bounds__(128) k_render_mega(DevScene s, float *__restrict__ accum, float *__restrict__ accum2, int n_spp, uint32_t seed, uint32_t first_sample,
                                                     int x0, int y0, int w, int h) {
     int tiles_x = (w + kDeTileW - 1) / kDeTileW;
     int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
@@ -23,26 +23,30 @@ __global__ void __launch_bounds__(128) k_render_mega(DevScene s, float *__restri
     cn.clear();
     size_t k = ((size_t)py * s.W + px) * 3;
     float3 acc = f3(accum[k], accum[k + 1], accum[k + 2]);
+    float3 acc2 = f3(0.0f, 0.0f, 0.0f);
     for (int sp = 0; sp < n_spp; ++sp) {
         float3 c = render_sample<COUNT, PREVIEW>(s, dv, px, py, first_sample + (uint32_t)sp, seed, cn, nullptr, nullptr);
         acc = acc + c;
+        acc2 = acc2 + c * c;
     }
     accum[k] = acc.x; accum[k + 1] = acc.y; accum[k + 2] = acc.z;
+    if (accum2) { accum2[k] += acc2.x; accum2[k + 1] += acc2.y; accum2[k + 2] += acc2.z; }  // second moments (image z-test), optional
     if (COUNT) cn.flush(s.counters);
 }
-void launch_render_mega(const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, bool count, cudaStream_t st) {
+void launch_render_mega(const DevScene &s, float *accum, float *accum2, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, bool count, cudaStream_t st) {
     int tiles = ((w + kDeTileW - 1) / kDeTileW) * ((h + kDeTileH - 1) / kDeTileH);
-    if (count) k_render_mega<true, false><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
-    else k_render_mega<false, false><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
+    if (count) k_render_mega<true, false><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h);
+    else k_render_mega<false, false><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h);
 }
 // the deterministic ray-marching preview (pathtracer.py:543-685) on the same film layout: every lane runs the same
 // 64 x 16 fixed-step loops, so one thread per pixel is already converged
-void launch_render_preview(const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, bool count, cudaStream_t st) {
+void launch_render_preview(const DevScene &s, float *accum, float *accum2, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, bool count, cudaStream_t st) {
     int tiles = ((w + kDeTileW - 1) / kDeTileW) * ((h + kDeTileH - 1) / kDeTileH);
-    if (count) k_render_mega<true, true><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
-    else k_render_mega<false, true><<<tiles, 128, 0, st>>>(s, accum, n_spp, seed, first_sample, x0, y0, w, h);
+    if (count) k_render_mega<true, true><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h);
+    else k_render_mega<false, true><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h);
 }
 
+#if DE_EXACT  // _render_to_image exists in IEEE source-order arithmetic only: every mode resolves through it
 // Renderer._render_to_image (renderer.py:346-365)
 __global__ void __launch_bounds__(256) k_resolve(DevScene s, const float *__restrict__ accum, float *__restrict__ out, int spp) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,6 +88,8 @@ void launch_resolve_peers(const DevScene &s, const float *accum, const float *co
     k_resolve_peers<<<(n + 255) / 256, 256, 0, st>>>(s, accum, pa, out, spp);
 }
 
+#endif  // DE_EXACT (resolve)
+
 #if !DE_EXACT
 // coarse max-map of the cloud texture: cell (cx,cy) = max over its cm_b x cm_b texels dilated by one
 __global__ void k_build_cloud_max(const uint8_t *tex, int w, int h, int b, uint8_t *out, int cw, int ch) {
@@ -99,6 +105,44 @@ __global__ void k_build_cloud_max(const uint8_t *tex, int w, int h, int b, uint8
 void launch_build_cloud_max(const uint8_t *tex, int w, int h, int b, uint8_t *out, int cw, int ch, cudaStream_t st) {
     k_build_cloud_max<<<(cw * ch + 127) / 128, 128, 0, st>>>(tex, w, h, b, out, cw, ch);
 }
+
+// ---- hooks on the PRODUCT flavour's work-removal bounds (the code the wavefront kernel runs, not a restatement) ----
+// cloud_pass_setup: out5 = (c_max of the footprint, density bound, t_start', t_max', 0)
+__global__ void k_fast_cloud_bound(int n, DevScene s, const float *pos, const float *dir, const float *ts, const float *tm, float *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 o = LD3(pos, i), d = LD3(dir, i);
+    float a = ts[i], b = tm[i];
+    out[4 * i] = cloud_segment_cmax(s, o, d, a, b);
+    out[4 * i + 1] = cloud_pass_setup(s, o, d, a, b);
+    out[4 * i + 2] = a; out[4 * i + 3] = b;
+}
+void t_fast_cloud_bound(const DevScene &s, const float *pos, const float *dir, const float *ts, const float *tm, float *out, int n, cudaStream_t st) {
+    k_fast_cloud_bound<<<(n + 127) / 128, 128, 0, st>>>(n, s, pos, dir, ts, tm, out);
+}
+// rmo_segment_majorant over [ts, tm] for extinctions ext3
+__global__ void k_fast_rmo_majorant(int n, const float *pos, const float *dir, const float *ts, const float *tm, const float *ext, float *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = rmo_segment_majorant(LD3(ext, i), LD3(pos, i), LD3(dir, i), ts[i], tm[i]);
+}
+void t_fast_rmo_majorant(const float *pos, const float *dir, const float *ts, const float *tm, const float *ext, float *out, int n, cudaStream_t st) {
+    k_fast_rmo_majorant<<<(n + 127) / 128, 128, 0, st>>>(n, pos, dir, ts, tm, ext, out);
+}
+// intersect_land of the product flavour: out3 = (1 if the prologue's miss test fired, intersection distance or -1, SDF evaluations)
+__global__ void k_fast_land(int n, DevScene s, const float *pos, const float *dir, float *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 o = LD3(pos, i), d = LD3(dir, i);
+    float ray_dist = 0.0f;
+    float2 rd = rsi(o, d, kAtmosUpper);
+    if (rd.x > 0.0f) ray_dist = rd.x;
+    Counters cn; cn.clear();
+    out[3 * i] = land_surely_missed(o + d * ray_dist, d, ray_dist, s.land_height_scale) ? 1.0f : 0.0f;
+    out[3 * i + 1] = intersect_land<true>(s, o, d, s.land_height_scale, cn);
+    out[3 * i + 2] = (float)cn.v[C_SDF];
+}
+void t_fast_land(const DevScene &s, const float *pos, const float *dir, float *out, int n, cudaStream_t st) { k_fast_land<<<(n + 127) / 128, 128, 0, st>>>(n, s, pos, dir, out); }
 #endif
 
 #if DE_EXACT

@@ -5,21 +5,24 @@
 struct DeWavefrontState;  // de_wavefront.cuh
 constexpr int kDeMaxPeers = 15;  // other ranks whose accumulation buffers one resolve can sum (16-GPU node)
 
-#define DE_DECLARE_COMMON                                                                                                              \
-    void launch_render_mega(const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w,  \
-                            int h, bool count, cudaStream_t st);                                                                       \
-    void launch_render_preview(const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0,      \
-                               int w, int h, bool count, cudaStream_t st);                                                            \
-    void launch_resolve(const DevScene &s, const float *accum, float *out, int spp, cudaStream_t st);                                 \
-    void launch_resolve_peers(const DevScene &s, const float *accum, const float *const *peers, int n_peers, float *out, int spp,     \
-                              cudaStream_t st);
+#define DE_DECLARE_COMMON                                                                                                                \
+    void launch_render_mega(const DevScene &s, float *accum, float *accum2, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, \
+                            int w, int h, bool count, cudaStream_t st);                                                                  \
+    void launch_render_preview(const DevScene &s, float *accum, float *accum2, int n_spp, uint32_t seed, uint32_t first_sample, int x0,     \
+                               int y0, int w, int h, bool count, cudaStream_t st);
 
 namespace de_fast {
 DE_DECLARE_COMMON
 void launch_build_cloud_max(const uint8_t *tex, int w, int h, int b, uint8_t *out, int cw, int ch, cudaStream_t st);
+// hooks on the product flavour's work-removal bounds (device pointers)
+void t_fast_cloud_bound(const DevScene &s, const float *pos, const float *dir, const float *ts, const float *tm, float *out4, int n, cudaStream_t st);
+void t_fast_rmo_majorant(const float *pos, const float *dir, const float *ts, const float *tm, const float *ext, float *out, int n, cudaStream_t st);
+void t_fast_land(const DevScene &s, const float *pos, const float *dir, float *out3, int n, cudaStream_t st);
 }
 namespace de_exact {
 DE_DECLARE_COMMON
+void launch_resolve(const DevScene &s, const float *accum, float *out, int spp, cudaStream_t st);
+void launch_resolve_peers(const DevScene &s, const float *accum, const float *const *peers, int n_peers, float *out, int spp, cudaStream_t st);
 void launch_prepare(const DevScene &s, DevDerived *out, cudaStream_t st);
 void launch_build_lambda(const DevScene &s, LambdaRow *lam, float *cdf, cudaStream_t st);
 // test hooks (parity arithmetic); all pointers are device pointers

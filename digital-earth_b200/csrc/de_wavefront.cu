@@ -95,15 +95,21 @@ struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
     int retired;     // slots that found no more work
     int phase;       // SM-wide preferred stage (WF_PHASE)
     int work_left;
+    unsigned int n_chunks;  // work units of this launch: tiles x samples x 4 quarter-tiles
+    unsigned int claimed;   // chunks this CTA claimed (timeline only)
 };
 
 struct WfParams {
     float *accum;
+    float *accum2;       // optional per-pixel second moments (sum of squared contributions), or nullptr
     unsigned int *next;  // global work counter (units of 32 paths)
-    unsigned int n_chunks;
+    const unsigned int *tile_list;  // film tiles this kernel renders (k_classify_tiles: everything that is not pure space)
+    const unsigned int *n_tiles;    // their number (device: the classification never syncs with the host)
     int n_spp, x0, y0, w, h, tiles_x;
     uint32_t seed, first_sample;
     unsigned long long *prof;  // counting build: per stage {cycles, visits, lanes}, + idle cycles at index ST_COUNT
+    unsigned long long *timeline;  // optional: globaltimer ns {first CTA start, first / last CTA to see the work counter exhausted,
+                                   // first / last CTA end, min / max chunks claimed by a CTA}
 };
 
 #ifndef WF_SPACE_SHORTCUT
@@ -154,6 +160,7 @@ __device__ __noinline__ uint4 philox_block(uint32_t k0, uint32_t k1, uint32_t c0
     }
     return make_uint4(c0, c1, c2, c3);
 }
+DE_DEV unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // Philox stream that can be resumed from (bounce, draw) kept in the pool
 struct RngW {
     uint32_t key0, key1, sample, bounce, draw;
@@ -420,11 +427,12 @@ template <bool COUNT> DE_DEV uint32_t stage_new(Ctx &c, int slot) {
     unsigned chunk = 0u;
     if (c.lane == 0) chunk = atomicAdd(P.next, 1u);
     chunk = __shfl_sync(full, chunk, 0);
-    if (chunk >= P.n_chunks) return ~0u;
-    // chunk = (tile * n_spp + sample) * 4 + quarter; kept in chunk units: the path index itself exceeds 32 bits for
-    // 4K x 4096 spp (3.4e10 paths)
+    if (chunk >= c.pool.n_chunks) return ~0u;
+    if (P.timeline && c.lane == 0) atomicAdd(&c.pool.claimed, 1u);
+    // chunk = (tile slot * n_spp + sample) * 4 + quarter; kept in chunk units: the path index itself exceeds 32 bits for
+    // 4K x 4096 spp (3.4e10 paths).  The tile comes from the list of tiles that can see the planet (k_classify_tiles).
     unsigned in_tile = (chunk & 3u) * 32u + (unsigned)c.lane, ts = chunk >> 2;
-    unsigned sp = ts % (unsigned)P.n_spp, tile = ts / (unsigned)P.n_spp;
+    unsigned sp = ts % (unsigned)P.n_spp, tile = __ldg(P.tile_list + ts / (unsigned)P.n_spp);
     int px = P.x0 + (int)(tile % (unsigned)P.tiles_x) * kDeTileW + (int)(in_tile & 15u);
     int py = P.y0 + (int)(tile / (unsigned)P.tiles_x) * kDeTileH + (int)(in_tile >> 4);
     if (px >= P.x0 + P.w || py >= P.y0 + P.h) return ST_NEW;
@@ -462,6 +470,10 @@ template <bool COUNT> WF_ENDPATH_ATTR uint32_t end_path(Ctx &c, int slot, uint32
         float3 rgb = xyz_to_rgb((Lr * f3(lr.resp_x, lr.resp_y, lr.resp_z)) * lr.rcp_pdf);
         float *a = c.P.accum + (size_t)c.pool.pix[slot] * 3;
         atomicAdd(a, rgb.x); atomicAdd(a + 1, rgb.y); atomicAdd(a + 2, rgb.z);
+        if (c.P.accum2) {  // per-pixel second moments for the image z-test; off in production
+            float *a2 = c.P.accum2 + (size_t)c.pool.pix[slot] * 3;
+            atomicAdd(a2, rgb.x * rgb.x); atomicAdd(a2 + 1, rgb.y * rgb.y); atomicAdd(a2 + 2, rgb.z * rgb.z);
+        }
     }
     return ST_NEW;
 }
@@ -812,7 +824,11 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         pool.q_head[threadIdx.x] = 0u;
         pool.q_avail[threadIdx.x] = threadIdx.x == ST_NEW ? WF_SLOTS : 0;
     }
-    if (threadIdx.x == 0) { pool.retired = 0; pool.work_left = 1; pool.phase = 0; }
+    if (threadIdx.x == 0) {
+        pool.retired = 0; pool.work_left = 1; pool.phase = 0; pool.claimed = 0u;
+        pool.n_chunks = __ldg(P.n_tiles) * (unsigned)P.n_spp * 4u;
+        if (P.timeline) atomicMin(&P.timeline[0], globaltimer_ns());
+    }
     __syncthreads();
     int last_st = -1;
     bool chained = false;  // the warp already holds slots of stage `st` (handed over by the previous one-shot stage)
@@ -880,7 +896,13 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
                 if (n < 32) { q_push_sorted(pool, has, ST_NEW, slot, lane); continue; }  // lost a race for a whole chunk
                 npk = stage_new<COUNT>(c, slot);
                 if (npk == ~0u) {  // work counter exhausted
-                    if (lane == 0) { pool.work_left = 0; atomicAdd(&pool.retired, 32); }
+                    if (lane == 0) {
+                        if (P.timeline && atomicExch(&pool.work_left, 0) != 0) {
+                            const unsigned long long tn = globaltimer_ns();
+                            atomicMin(&P.timeline[1], tn); atomicMax(&P.timeline[2], tn);
+                        }
+                        pool.work_left = 0; atomicAdd(&pool.retired, 32);
+                    }
                     continue;
                 }
             } else if (has) {
@@ -929,6 +951,146 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         }
     }
     if (COUNT) cn.flush(s.counters);
+    if (P.timeline) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long tn = globaltimer_ns();
+            atomicMin(&P.timeline[3], tn); atomicMax(&P.timeline[4], tn);
+            atomicMin(&P.timeline[5], (unsigned long long)pool.claimed); atomicMax(&P.timeline[6], (unsigned long long)pool.claimed);
+        }
+    }
+}
+
+
+
+// ------------------------------------------------------------------ film tiles that cannot see the planet
+// Apollo 11 (BASELINE configs[1]): 63 % of the samples are primary rays that miss the atmosphere shell.  They interact with
+// nothing (pathtracer.py:441-444,455-466: sun disc + star map), so a tile ALL of whose jittered primary rays miss the
+// 6 481 km shell needs no path state, no queues and no scheduler: k_space_tiles renders its samples one thread per pixel,
+// fully converged, and the persistent kernel only receives the list of the remaining tiles.
+//
+// Classification (f64, one thread per tile, ordered compaction so the work order is deterministic): the rays of a tile are
+// dir(px, py) over the rectangle [x, x+16] x [y, y+8] of continuous film coordinates (pixel + jitter in [0,1), renderer.py:
+// 269-279).  Seen from a camera outside the shell the hit directions form the cap of half-angle asin(R_atm / |cam|) around
+// -cam.  All rays of the tile lie within alpha = max corner angle of the tile-centre direction (the sub-level sets of the
+// angular distance are convex in the film plane, so its maximum over a rectangle sits on a corner); the tile is space iff
+// angle(centre, -cam) > cap + alpha + 2e-5 rad.  The margin is ~30x the f32 rounding of get_cast_dir / rsi at |cam| = 5.7e7 m
+// (where 2e-5 rad = 1.1 km): every sample of a space tile is also a miss of the reference's own f32 test, so the samples
+// are the same paths with the same values as the generic route (tests/test_gpu_render.py compares the two bit patterns).
+struct D3 { double x, y, z; };
+DE_DEV D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
+DE_DEV double ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+DE_DEV D3 dcross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+DE_DEV double dangle(D3 a, D3 b) { D3 c = dcross(a, b); return atan2(sqrt(ddot(c, c)), ddot(a, b)); }
+DE_DEV D3 film_dir(const DevScene &s, const DevDerived &dv, double px, double py) {  // get_cast_dir before normalisation
+    const double fov = s.fov;
+    const double fu = (2.0 * fov * px / (double)s.H - fov * (double)s.aspect_ratio - 1e-5) * (double)s.aspect_scale;
+    const double fv = 2.0 * fov * py / (double)s.H - fov - 1e-5;
+    return d3(dv.cam_d.x + fu * dv.cam_du.x + fv * dv.cam_dv.x, dv.cam_d.y + fu * dv.cam_du.y + fv * dv.cam_dv.y,
+              dv.cam_d.z + fu * dv.cam_du.z + fv * dv.cam_dv.z);
+}
+DE_DEV bool tile_is_space(const DevScene &s, const DevDerived &dv, int x0, int y0, int x1, int y1) {
+    const D3 cam = d3(s.cam_pos.x, s.cam_pos.y, s.cam_pos.z);
+    const double dist = sqrt(ddot(cam, cam));
+    if (!(dist > (double)kAtmosUpper * 1.0001)) return false;  // camera inside (or grazing) the shell: every ray is in the medium
+    const double cap = asin((double)kAtmosUpper / dist);
+    const D3 axis = d3(-cam.x, -cam.y, -cam.z);
+    const D3 c = film_dir(s, dv, 0.5 * (x0 + x1), 0.5 * (y0 + y1));
+    double alpha = dangle(c, film_dir(s, dv, x0, y0));
+    alpha = fmax(alpha, dangle(c, film_dir(s, dv, x1, y0)));
+    alpha = fmax(alpha, dangle(c, film_dir(s, dv, x0, y1)));
+    alpha = fmax(alpha, dangle(c, film_dir(s, dv, x1, y1)));
+    const double phi = dangle(c, axis);
+    return phi > cap + alpha + 2e-5;  // NaN (degenerate camera) compares false: generic route
+}
+// one CTA; cls[t] = 1 for space tiles, wf_list = the others in tile order, counts = {n_wf, n_space}
+__global__ void __launch_bounds__(1024) k_classify_tiles(const __grid_constant__ DevScene s, int x0, int y0, int w, int h, int tiles_x, int n_tiles, int enable,
+                                                        unsigned char *cls, unsigned int *wf_list, unsigned int *counts) {
+    __shared__ unsigned int warp_sum[32];
+    __shared__ unsigned int base_wf;
+    const DevDerived dv = *s.derived;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_wf = 0u;
+    __syncthreads();
+    for (int b = 0; b < n_tiles; b += 1024) {
+        const int t = b + (int)threadIdx.x;
+        bool keep = false;
+        if (t < n_tiles) {
+            const int tx = t % tiles_x, ty = t / tiles_x;
+            const int px0 = x0 + tx * kDeTileW, py0 = y0 + ty * kDeTileH;
+            const bool space = enable && tile_is_space(s, dv, px0, py0, min(px0 + kDeTileW, x0 + w), min(py0 + kDeTileH, y0 + h));
+            cls[t] = space ? 1 : 0;
+            keep = !space;
+        }
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+        if (lane == 0) warp_sum[wid] = __popc(bal);
+        __syncthreads();
+        unsigned int off = base_wf;
+        for (int k = 0; k < wid; ++k) off += warp_sum[k];
+        if (keep) wf_list[off + __popc(bal & ((1u << lane) - 1u))] = (unsigned)t;
+        __syncthreads();
+        if (threadIdx.x == 0) { unsigned int tot = 0u; for (int k = 0; k < 32; ++k) tot += warp_sum[k]; base_wf += tot; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { counts[0] = base_wf; counts[1] = (unsigned)n_tiles - base_wf; }
+}
+
+// Renderer.render for tiles that cannot see the planet: one thread per pixel, n samples in registers, one add per pixel.
+// Same random stream, same expressions as stage_new + end_path(primary_miss), minus the (certainly failing) shell test.
+#ifndef WF_SPACE_SPLIT
+#define WF_SPACE_SPLIT 64  // samples per CTA: enough CTAs at low spp, 3 atomics per pixel and 64 samples at high spp
+#endif
+template <bool COUNT> __global__ void __launch_bounds__(kDeTileW * kDeTileH) k_space_tiles(const __grid_constant__ DevScene s, const __grid_constant__ WfParams P,
+                                                                                            const unsigned char *__restrict__ cls) {
+    const unsigned tile = blockIdx.x;
+    if (!cls[tile]) return;
+    __shared__ float cdf_s[kLambdaBins];
+    for (int k = threadIdx.x; k < kLambdaBins; k += blockDim.x) cdf_s[k] = s.cdf[k];
+    __syncthreads();
+    const int px = P.x0 + (int)(tile % (unsigned)P.tiles_x) * kDeTileW + (int)(threadIdx.x & 15u);
+    const int py = P.y0 + (int)(tile / (unsigned)P.tiles_x) * kDeTileH + (int)(threadIdx.x >> 4);
+    if (px >= P.x0 + P.w || py >= P.y0 + P.h) return;
+    const DevDerived dv = *s.derived;
+    const uint32_t pix = (uint32_t)(py * s.W + px);
+    const int s0 = (int)blockIdx.y * WF_SPACE_SPLIT, s1 = min(s0 + WF_SPACE_SPLIT, P.n_spp);
+    float3 acc = f3(0.0f, 0.0f, 0.0f), acc2 = f3(0.0f, 0.0f, 0.0f);
+    unsigned ntex = 0u;
+#pragma unroll 1
+    for (int sp = s0; sp < s1; ++sp) {
+        const uint4 b = philox_block(P.seed, pix, P.first_sample + (uint32_t)sp, 0u, 0u);
+        const int bin = spectrum_bin(cdf_s, u32_to_unit(b.x));
+        const float3 dir = get_cast_dir(s, dv, (float)px, (float)py, u32_to_unit(b.y), u32_to_unit(b.z));
+        const LambdaRow &lr = s.lam[bin];
+        float Lr = 0.0f;
+        if (dot(dv.light_dir, dir) > dv.sun_cos_angle) Lr += lr.sun_power;
+        ++ntex;
+        const float3 st = sample_sphere_rgb8(s.tex[6], dir);
+        const float stars_power = lr.s2s_valid != 0.0f ? dot(st, f3(lr.s2s_r, lr.s2s_g, lr.s2s_b)) : 0.0f;
+        Lr += stars_power * lr.sun_power * 0.0000001f;
+        if (isinf(Lr) || isnan(Lr) || Lr < 0.0f) Lr = 0.0f;
+        if (Lr != 0.0f) {
+            const float3 rgb = xyz_to_rgb((Lr * f3(lr.resp_x, lr.resp_y, lr.resp_z)) * lr.rcp_pdf);
+            acc = acc + rgb;
+            acc2 = acc2 + rgb * rgb;
+        }
+    }
+    if (acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f) {
+        float *a = P.accum + (size_t)pix * 3;
+        atomicAdd(a, acc.x); atomicAdd(a + 1, acc.y); atomicAdd(a + 2, acc.z);
+        if (P.accum2) {
+            float *a2 = P.accum2 + (size_t)pix * 3;
+            atomicAdd(a2, acc2.x); atomicAdd(a2 + 1, acc2.y); atomicAdd(a2 + 2, acc2.z);
+        }
+    }
+    if (COUNT && s.counters) {  // same bookkeeping as the generic route: one segment and one star fetch per path
+        const unsigned n = (unsigned)(s1 - s0);
+        const unsigned tot = __reduce_add_sync(__activemask(), n), tt = __reduce_add_sync(__activemask(), ntex);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(__activemask()) - 1)) {
+            atomicAdd(&s.counters[C_PATHS], (unsigned long long)tot);
+            atomicAdd(&s.counters[C_SEGMENTS], (unsigned long long)tot);
+            atomicAdd(&s.counters[C_TEX], (unsigned long long)tt);
+        }
+    }
 }
 
 }  // namespace de_fast
@@ -936,8 +1098,17 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
 struct DeWavefrontState {
     int device = 0, sm_count = 0;
     unsigned int *d_next = nullptr;
-    unsigned long long *d_prof = nullptr;
+    unsigned long long *d_prof = nullptr;      // [0,32): stage profile, [32,40): launch timeline
     bool attr_set = false;
+    // tile classification, cached per (parameter version, window)
+    unsigned char *d_cls = nullptr;
+    unsigned int *d_wf_list = nullptr, *d_counts = nullptr;
+    int tiles_cap = 0;
+    unsigned long long cls_version = ~0ull;
+    int cls_win[4] = {-1, -1, -1, -1}, cls_enable = -1;
+    // k_space_tiles runs on a side stream so its CTAs fill the SMs the persistent kernel's drain leaves idle
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 DeWavefrontState *de_wavefront_alloc(int device) {
@@ -945,18 +1116,27 @@ DeWavefrontState *de_wavefront_alloc(int device) {
     st->device = device;
     cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (cudaMalloc(&st->d_next, sizeof(unsigned int)) != cudaSuccess) { delete st; return nullptr; }
-    if (cudaMalloc(&st->d_prof, sizeof(unsigned long long) * 32) != cudaSuccess) { cudaFree(st->d_next); delete st; return nullptr; }
-    cudaMemset(st->d_prof, 0, sizeof(unsigned long long) * 32);
+    if (cudaMalloc(&st->d_prof, sizeof(unsigned long long) * 40) != cudaSuccess) { cudaFree(st->d_next); delete st; return nullptr; }
+    if (cudaMalloc(&st->d_counts, sizeof(unsigned int) * 2) != cudaSuccess) { cudaFree(st->d_next); cudaFree(st->d_prof); delete st; return nullptr; }
+    cudaMemset(st->d_prof, 0, sizeof(unsigned long long) * 40);
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = numerically greatest = lowest priority
+    if (cudaStreamCreateWithPriority(&st->side, cudaStreamNonBlocking, lo) != cudaSuccess) st->side = nullptr;
+    if (cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming) != cudaSuccess) st->ev_fork = nullptr;
+    if (cudaEventCreateWithFlags(&st->ev_join, cudaEventDisableTiming) != cudaSuccess) st->ev_join = nullptr;
     return st;
 }
 void de_wavefront_free(DeWavefrontState *st) {
     if (!st) return;
     cudaFree(st->d_next);
     cudaFree(st->d_prof);
+    cudaFree(st->d_cls); cudaFree(st->d_wf_list); cudaFree(st->d_counts);
+    if (st->side) cudaStreamDestroy(st->side);
+    if (st->ev_fork) cudaEventDestroy(st->ev_fork);
+    if (st->ev_join) cudaEventDestroy(st->ev_join);
     delete st;
 }
-void de_wavefront_render(DeWavefrontState *st, const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0,
-                         int w, int h, bool count, cudaStream_t stream) {
+int de_wavefront_render(DeWavefrontState *st, const DevScene &s, const DeWavefrontJob &job, cudaStream_t stream) {
     using namespace de_fast;
     size_t smem = sizeof(WarpPool);
     if (!st->attr_set) {
@@ -965,26 +1145,61 @@ void de_wavefront_render(DeWavefrontState *st, const DevScene &s, float *accum, 
         st->attr_set = true;
     }
     WfParams P;
-    P.accum = accum; P.next = st->d_next;
-    P.tiles_x = (w + kDeTileW - 1) / kDeTileW;
-    const long long tiles = (long long)P.tiles_x * ((h + kDeTileH - 1) / kDeTileH);
-    P.x0 = x0; P.y0 = y0; P.w = w; P.h = h; P.seed = seed;
+    P.accum = job.accum; P.accum2 = job.accum2; P.next = st->d_next;
+    P.tiles_x = (job.w + kDeTileW - 1) / kDeTileW;
+    const long long tiles = (long long)P.tiles_x * ((job.h + kDeTileH - 1) / kDeTileH);
+    P.x0 = job.x0; P.y0 = job.y0; P.w = job.w; P.h = job.h; P.seed = job.seed;
+    const bool count = job.count;
     P.prof = count ? st->d_prof : nullptr;
+    P.timeline = job.timeline ? st->d_prof + 32 : nullptr;
     if (count) cudaMemsetAsync(st->d_prof, 0, sizeof(unsigned long long) * 32, stream);
+    if (job.timeline) {
+        const unsigned long long init[8] = {~0ull, ~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull};
+        cudaMemcpyAsync(st->d_prof + 32, init, sizeof(init), cudaMemcpyHostToDevice, stream);  // pageable source: staged before the call returns
+    }
+    // tiles that cannot see the planet go to k_space_tiles; the classification only changes with the camera or the window
+    if ((int)tiles > st->tiles_cap) {
+        cudaFree(st->d_cls); cudaFree(st->d_wf_list);
+        st->d_cls = nullptr; st->d_wf_list = nullptr; st->tiles_cap = 0;
+        if (cudaMalloc(&st->d_cls, (size_t)tiles) != cudaSuccess || cudaMalloc(&st->d_wf_list, (size_t)tiles * sizeof(unsigned int)) != cudaSuccess) return -1;
+        st->tiles_cap = (int)tiles;
+        st->cls_version = ~0ull;
+    }
+    const int enable = job.space_tiles ? 1 : 0;
+    if (st->cls_version != job.param_version || st->cls_win[0] != job.x0 || st->cls_win[1] != job.y0 || st->cls_win[2] != job.w || st->cls_win[3] != job.h ||
+        st->cls_enable != enable) {
+        k_classify_tiles<<<1, 1024, 0, stream>>>(s, job.x0, job.y0, job.w, job.h, P.tiles_x, (int)tiles, enable, st->d_cls, st->d_wf_list, st->d_counts);
+        st->cls_version = job.param_version; st->cls_enable = enable;
+        st->cls_win[0] = job.x0; st->cls_win[1] = job.y0; st->cls_win[2] = job.w; st->cls_win[3] = job.h;
+    }
+    P.tile_list = st->d_wf_list; P.n_tiles = st->d_counts;
     // the work counter is 32 bits wide: at most 2^31 chunks (2^36 paths) per launch, more samples go in several launches
     const long long max_spp = ((1LL << 31) / (tiles * 4) > 1) ? (1LL << 31) / (tiles * 4) : 1;
-    for (long long done = 0; done < n_spp; done += max_spp) {
-        const int batch = (int)((n_spp - done < max_spp) ? n_spp - done : max_spp);
-        P.n_chunks = (unsigned)(tiles * batch * 4);
-        P.n_spp = batch; P.first_sample = first_sample + (uint32_t)done;
+    for (long long done = 0; done < job.n_spp; done += max_spp) {
+        const int batch = (int)((job.n_spp - done < max_spp) ? job.n_spp - done : max_spp);
+        P.n_spp = batch; P.first_sample = job.first_sample + (uint32_t)done;
         cudaMemsetAsync(st->d_next, 0, sizeof(unsigned int), stream);
+        const bool async = enable && job.space_async && st->side && st->ev_fork && st->ev_join;
+        cudaStream_t sstream = async ? st->side : stream;
+        if (async) { cudaEventRecord(st->ev_fork, stream); cudaStreamWaitEvent(st->side, st->ev_fork, 0); }
         const int grid = st->sm_count;
         if (count) k_render_wavefront<true><<<grid, WF_WARPS * 32, smem, stream>>>(s, P);
         else k_render_wavefront<false><<<grid, WF_WARPS * 32, smem, stream>>>(s, P);
+        if (enable) {  // (disjoint pixels: the two kernels never touch the same accumulator)
+            const dim3 sg((unsigned)tiles, (unsigned)((batch + WF_SPACE_SPLIT - 1) / WF_SPACE_SPLIT));
+            if (count) k_space_tiles<true><<<sg, kDeTileW * kDeTileH, 0, sstream>>>(s, P, st->d_cls);
+            else k_space_tiles<false><<<sg, kDeTileW * kDeTileH, 0, sstream>>>(s, P, st->d_cls);
+        }
+        if (async) { cudaEventRecord(st->ev_join, st->side); cudaStreamWaitEvent(stream, st->ev_join, 0); }
     }
+    return 0;
 }
 
-int de_wavefront_profile(DeWavefrontState *st, unsigned long long *out32) {
+int de_wavefront_profile(DeWavefrontState *st, unsigned long long *out40) {
     if (!st) return -1;
-    return cudaMemcpy(out32, st->d_prof, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+    return cudaMemcpy(out40, st->d_prof, sizeof(unsigned long long) * 40, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+int de_wavefront_tile_counts(DeWavefrontState *st, unsigned int *out2) {
+    if (!st) return -1;
+    return cudaMemcpy(out2, st->d_counts, sizeof(unsigned int) * 2, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }

@@ -3,9 +3,21 @@
 #include "de_scene.h"
 
 struct DeWavefrontState;
+struct DeWavefrontJob {
+    float *accum = nullptr, *accum2 = nullptr;  // [H][W][3] sums and (optional) sums of squares
+    int n_spp = 1;
+    uint32_t seed = 0, first_sample = 0;
+    int x0 = 0, y0 = 0, w = 0, h = 0;
+    bool count = false;        // counting build: event counters + per-stage cycle profile
+    bool timeline = false;     // record the launch timeline (ramp / drain), see de_get_launch_timeline
+    bool space_tiles = true;   // render tiles that cannot see the planet in k_space_tiles
+    bool space_async = true;   // ... on a low-priority side stream, overlapping the persistent kernel's drain
+    unsigned long long param_version = 0;  // bumps whenever the camera changes (tile classification cache)
+};
 DeWavefrontState *de_wavefront_alloc(int device);
 void de_wavefront_free(DeWavefrontState *st);
-void de_wavefront_render(DeWavefrontState *st, const DevScene &s, float *accum, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0,
-                         int w, int h, bool count, cudaStream_t stream);
-// counting build only: out32[3*stage + {0,1,2}] = {cycles, visits, slots} per stage, out32[3*ST_COUNT] = idle cycles (warp-level sums)
-int de_wavefront_profile(DeWavefrontState *st, unsigned long long *out32);
+int de_wavefront_render(DeWavefrontState *st, const DevScene &s, const DeWavefrontJob &job, cudaStream_t stream);
+// out40[3*stage + {0,1,2}] = {cycles, visits, slots} per stage (counting build), out40[3*ST_COUNT] = idle cycles (warp-level sums);
+// out40[32..38] = launch timeline in globaltimer ns / chunks (DeWavefrontJob::timeline)
+int de_wavefront_profile(DeWavefrontState *st, unsigned long long *out40);
+int de_wavefront_tile_counts(DeWavefrontState *st, unsigned int *out2);  // {tiles in the persistent kernel, space tiles}

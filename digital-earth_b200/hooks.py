@@ -80,3 +80,8 @@ class Hooks:
     def trace_preview(self, px, py, sample, seed): return self._call("de_test_trace_preview", len(px), (len(px), 5), self.i(px), self.i(py), self.u(sample), C.c_uint32(seed))
     def ray_march(self, pos, direction, t0, t1, sun, wl): return self._call("de_test_ray_march", len(pos), (len(pos), 2), self.f(pos), self.f(direction), self.f(t0), self.f(t1), self.f(sun), self.f(wl))
     def trace_paths(self, px, py, sample, seed): return self._call("de_test_trace_paths", len(px), (len(px), 5), self.i(px), self.i(py), self.u(sample), C.c_uint32(seed))
+
+    # product-flavour work-removal bounds (the device functions the wavefront kernel calls)
+    def fast_cloud_bound(self, pos, d, ts, tm): return self._call("de_test_fast_cloud_bound", len(ts), (len(ts), 4), self.f(pos), self.f(d), self.f(ts), self.f(tm))
+    def fast_rmo_majorant(self, pos, d, ts, tm, ext): return self._call("de_test_fast_rmo_majorant", len(ts), (len(ts),), self.f(pos), self.f(d), self.f(ts), self.f(tm), self.f(ext))
+    def fast_land(self, pos, d): return self._call("de_test_fast_land", len(pos), (len(pos), 3), self.f(pos), self.f(d))

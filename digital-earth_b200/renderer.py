@@ -37,8 +37,28 @@ class _Field0:
         self._owner._dirty = True
 
 
+class _CtxHandle:
+    """Owns the libde context.  Shared by the Renderer and by every tensor that views context-owned device memory, so the
+    context (and the memory) lives exactly as long as its last user: a `color_buffer` tensor kept after `Renderer.close()`
+    stays valid, and the context is destroyed when that tensor goes away."""
+
+    def __init__(self, lib, ctx):
+        self.lib, self.ctx = lib, ctx
+
+    def __del__(self):
+        try:
+            if self.ctx is not None and self.ctx.value:
+                self.lib.de_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+
 class _CudaView:
-    def __init__(self, ptr, shape):
+    """__cuda_array_interface__ wrapper; torch keeps this object (hence the context handle) alive with the storage."""
+
+    def __init__(self, ptr, shape, handle):
+        self._handle = handle
         self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": "<f4", "version": 2, "strides": None}
 
 
@@ -66,6 +86,8 @@ class Renderer:
         rc = self._lib.de_create(C.byref(self._ctx), self.device.index, self.image_res[0], self.image_res[1])
         if rc != 0:
             raise _lib.DeError("de_create failed (%d)" % rc)
+        self._handle = _CtxHandle(self._lib, self._ctx)
+        self._moment2 = None
         self.set_mode(mode)
 
         # 0-d fields (renderer.py:27-41) with the defaults of renderer.py:49-56
@@ -106,22 +128,49 @@ class Renderer:
         self._image = torch.empty((self.image_res[1], self.image_res[0], 3), dtype=torch.float32, device=self.device)
         ptr = C.c_void_p()
         self._check(self._lib.de_get_accum(self._ctx, C.byref(ptr)))
-        self._accum = torch.as_tensor(_CudaView(ptr.value, (self.image_res[1], self.image_res[0], 3)), device=self.device)
+        self._accum = torch.as_tensor(_CudaView(ptr.value, (self.image_res[1], self.image_res[0], 3), self._handle), device=self.device)
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc):
         _lib.check(self._ctx, rc)
 
     def close(self):
-        if getattr(self, "_ctx", None) is not None and self._ctx.value:
-            self._lib.de_destroy(self._ctx)
-            self._ctx = C.c_void_p()
+        """Release the context.  Tensors handed out earlier (`color_buffer`, `moment2`) keep it alive until they die."""
+        self._accum = self._moment2 = self._handle = None
+        self._ctx = C.c_void_p()
 
     def __del__(self):
         try:
             self.close()
         except Exception:
             pass
+
+    def set_option(self, name, value):
+        """Integrator options of include/de_api.h (`space_tiles`, `space_async`, `moments`, `timeline`, `linear_textures`)."""
+        self._bind_stream()
+        self._check(self._lib.de_set_option(self._ctx, str(name).encode(), int(value)))
+        if name == "moments":
+            self._moment2 = None
+
+    @property
+    def moment2(self):
+        """Per-pixel sums of squared sample contributions [H][W][3] (option `moments`): with `color_buffer` the sample
+        variance of every pixel, for the image z-test of SURVEY 8d."""
+        if self._moment2 is None:
+            ptr = C.c_void_p()
+            self._check(self._lib.de_get_moment2(self._ctx, C.byref(ptr)))
+            self._moment2 = self._torch.as_tensor(_CudaView(ptr.value, (self.image_res[1], self.image_res[0], 3), self._handle), device=self.device)
+        return self._moment2
+
+    def launch_timeline(self):
+        """Timeline of the last wavefront accumulate() with option `timeline` (ms relative to the first CTA's start)."""
+        buf = np.zeros(8, np.uint64)
+        self._check(self._lib.de_get_launch_timeline(self._ctx, buf.ctypes.data_as(C.c_void_p)))
+        t0 = int(buf[0])
+        ms = lambda k: (int(buf[k]) - t0) * 1e-6  # noqa: E731
+        return {"first_exhaust_ms": ms(1), "last_exhaust_ms": ms(2), "first_cta_end_ms": ms(3), "last_cta_end_ms": ms(4),
+                "min_chunks_per_cta": int(buf[5]), "max_chunks_per_cta": int(buf[6]),
+                "wavefront_tiles": int(buf[7]) & 0xFFFFFFFF, "space_tiles": int(buf[7]) >> 32}
 
     def set_mode(self, mode):
         """'wavefront' (product), 'megakernel' (1 thread/pixel baseline) or 'parity' (IEEE source-order)."""

@@ -101,6 +101,15 @@ const char *de_last_error(de_ctx *ctx);
 int de_set_stream(de_ctx *ctx, void *cuda_stream);
 int de_set_mode(de_ctx *ctx, int mode);
 
+/* integrator options (name, value); unknown names fail with DE_ERR_INVALID:
+ *   "space_tiles"     1 (default) film tiles that cannot see the atmosphere shell are rendered by a dedicated converged kernel
+ *   "space_async"     1 (default) ... on a side stream, overlapping the persistent kernel's drain
+ *   "moments"         1 = keep per-pixel sums of squared sample contributions beside the accumulation buffer (image z-test,
+ *                     SURVEY 8d); de_get_moment2 returns the buffer; de_reset clears it
+ *   "timeline"        1 = record the wavefront kernel's launch timeline (de_get_launch_timeline)
+ *   "linear_textures" 0 = release the row-major texture copies (read by the parity flavour and the hooks only) */
+int de_set_option(de_ctx *ctx, const char *name, int value);
+
 /* the eleven set_* kernels + direct field writes  renderer.py:224-266, earth_viewer.py:308-314 */
 int de_set_params(de_ctx *ctx, const DeParams *p);
 
@@ -119,6 +128,8 @@ int de_accumulate(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, 
 /* device pointer of the accumulation buffer ([H][W][3] f32 linear sRGB sums; color_buffer,
  * renderer.py:25,330) so the caller can view it as a tensor / hand it to NCCL */
 int de_get_accum(de_ctx *ctx, float **dev_ptr);
+/* second-moment buffer ([H][W][3] f32 sums of squared per-sample RGB contributions), option "moments" */
+int de_get_moment2(de_ctx *ctx, float **dev_ptr);
 /* Renderer.fetch_image == _render_to_image kernel  renderer.py:346-365,382-384.
  * dev_out: device [H][W][3] f32 in [0,1].  accum_override (device, may be NULL) resolves another
  * buffer of the same shape, e.g. an NCCL-reduced one. */
@@ -149,6 +160,11 @@ int de_set_counting(de_ctx *ctx, int enabled);     /* counters cost atomics: off
  * visits and slots handled by stage s (NEW, SDF, RMO, CLOUD, SDF_DONE, RMO_DONE, EVENT, NEE_DONE, SURFACE), out32[27] = idle cycles */
 int de_get_stage_profile(de_ctx *ctx, uint64_t *out32);
 
+/* launch timeline of the last de_accumulate in wavefront mode with option "timeline" (synchronises): globaltimer ns
+ * out8 = {first CTA start, first CTA to find the work counter exhausted, last CTA to, first CTA end, last CTA end,
+ *         min chunks claimed by a CTA, max chunks, (space tiles << 32) | tiles rendered by the persistent kernel} */
+int de_get_launch_timeline(de_ctx *ctx, uint64_t *out8);
+
 /* ---- test hooks: the deterministic sub-paths of SURVEY 8(a), DEVICE pointers, n items --------
  * Each evaluates the IEEE source-order (parity) flavour of one reference function. */
 int de_test_philox(de_ctx *, const uint32_t *ctr4_key2, uint32_t *out4, int n);
@@ -178,6 +194,14 @@ int de_test_tracking(de_ctx *, int kind, const float *pos3, const float *dir3, c
 /* individual path samples in PARITY arithmetic: out5 = rgb contribution, wavelength, radiance   renderer.py:305-330 */
 int de_test_ray_march(de_ctx *, const float *pos3, const float *dir3, const float *t0, const float *t1, const float *sun3, const float *wavelength, float *out2, int n); /* pathtracer.py:501-541 */
 int de_test_trace_preview(de_ctx *, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out5, int n); /* renderer.py:305-330 with pathtracer.py:543-685 */
+/* ---- hooks on the PRODUCT flavour's work-removal bounds: the very device functions the wavefront kernel calls
+ * (csrc/de_device.cuh), so their validity can be checked ray by ray against dense samples of the oracle -------------- */
+/* cloud_pass_setup over [t_start, t_max]: out4 = (texture bound c_max, density bound (0 = skip the pass), t_start', t_max') */
+int de_test_fast_cloud_bound(de_ctx *, const float *pos3, const float *dir3, const float *t_start, const float *t_max, float *out4, int n);
+/* rmo_segment_majorant: bound of sigma.rho (extinctions ext3) over [t_start, t_max] */
+int de_test_fast_rmo_majorant(de_ctx *, const float *pos3, const float *dir3, const float *t_start, const float *t_max, const float *ext3, float *out, int n);
+/* product-flavour intersect_land: out3 = (1 if land_surely_missed fired, distance or -1, SDF evaluations) */
+int de_test_fast_land(de_ctx *, const float *pos3, const float *dir3, float *out3, int n);
 int de_test_trace_paths(de_ctx *, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out5, int n);
 
 #if defined(__GNUC__)

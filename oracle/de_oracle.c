@@ -1269,6 +1269,14 @@ ORC_API void orc_resolve(const orc_scene *s, const float *accum, int samples, fl
 ORC_API void orc_intersect_land(int n, const orc_scene *s, const float *pos, const float *dir, float *out) {
     for (int i = 0; i < n; ++i) out[i] = intersect_land(s, LD3(pos, i), LD3(dir, i), s->land_height_scale, NULL);
 }
+/* out[2n] = (distance or -1, SDF evaluations): 250 evaluations with a hit = the march ran into its iteration cap */
+ORC_API void orc_intersect_land_iters(int n, const orc_scene *s, const float *pos, const float *dir, float *out) {
+    for (int i = 0; i < n; ++i) {
+        orc_counters c; memset(&c, 0, sizeof c);
+        out[2 * i] = intersect_land(s, LD3(pos, i), LD3(dir, i), s->land_height_scale, &c);
+        out[2 * i + 1] = (float)c.sdf_evals;
+    }
+}
 ORC_API void orc_land_normal(int n, const orc_scene *s, const float *pos, float *out) {
     for (int i = 0; i < n; ++i) { v3 o = land_normal(s, LD3(pos, i), s->land_height_scale, NULL); ST3(out, i, o); }
 }

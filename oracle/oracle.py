@@ -119,16 +119,26 @@ def philox(ctr, key):
 
 
 def _call(name, n, out_shape, *args):
+    """Batch entry points are plain loops over n items; big batches are cut into row blocks run on host threads
+    (ctypes releases the GIL).  Per-item results do not depend on the cut: no item reads another's state."""
     out = np.zeros(out_shape, dtype=np.float32)
-    conv = []
-    keep = []
-    for a in args:
-        if isinstance(a, np.ndarray):
-            keep.append(a)
-            conv.append(_p(a))
-        else:
-            conv.append(a)
-    getattr(lib(), name)(C.c_int(n), *conv, _p(out))
+    fn = getattr(lib(), name)
+    per_item = name not in ("orc_tracking",)      # its Philox key is the item index
+    nthr = min(os.cpu_count() or 1, 32)
+    if per_item and n >= 50000 and nthr > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        edges = np.linspace(0, n, nthr + 1).astype(int)
+
+        def run(k):
+            a, b = int(edges[k]), int(edges[k + 1])
+            if b > a:
+                sl = [_p(np.ascontiguousarray(x[a:b])) if isinstance(x, np.ndarray) and x.ndim >= 1 and x.shape[0] == n else (_p(x) if isinstance(x, np.ndarray) else x) for x in args]
+                fn(C.c_int(b - a), *sl, _p(out[a:b]))
+        with ThreadPoolExecutor(nthr) as ex:
+            list(ex.map(run, range(nthr)))
+        return out
+    conv = [_p(a) if isinstance(a, np.ndarray) else a for a in args]
+    fn(C.c_int(n), *conv, _p(out))
     return out
 
 
@@ -237,6 +247,12 @@ def resolve(scene, accum, samples):
 def intersect_land(scene, pos, dirs):
     pos, dirs = _f32(pos), _f32(dirs)
     return _call("orc_intersect_land", len(pos), (len(pos),), scene.ref, pos, dirs)
+
+
+def intersect_land_iters(scene, pos, dirs):
+    """(distance or -1, SDF evaluations) per ray; 250 evaluations and a hit = the reference's iteration-cap artefact."""
+    pos, dirs = _f32(pos), _f32(dirs)
+    return _call("orc_intersect_land_iters", len(pos), (len(pos), 2), scene.ref, pos, dirs)
 
 
 def land_normal(scene, pos):

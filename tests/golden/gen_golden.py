@@ -400,7 +400,7 @@ def main():
         cur["s"].set_bounce(cur["s"].bounce + 1)
         return orig_si(*a, **k)
     pt.sample_interaction = hooked
-    n_per = int(os.environ.get("DE_GOLDEN_PATHS", "40"))
+    n_per = int(os.environ.get("DE_GOLDEN_PATHS", "64"))  # the committed fixture holds 64 per view
     for cname, cfg in cfgs.items():
         key = cname.split()[0].lower()
         apply_config(R, cfg)
@@ -434,7 +434,7 @@ def main():
     # Random123 known-answer vectors for Philox4x32-10
     G["philox_kat"] = np.array([philox4x32_10((0, 0, 0, 0), (0, 0)), philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2),
                                 philox4x32_10((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0))], np.uint32)
-    outp = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
+    outp = os.environ.get("DE_GOLDEN_OUT") or os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
     np.savez_compressed(outp, **G)
     print("wrote %s (%d arrays, %.1f kB) in %.1fs" % (outp, len(G), os.path.getsize(outp) / 1e3, time.time() - t_all))
 

@@ -58,7 +58,7 @@ def main():
     # ---- whole preview samples: Renderer.render's prologue (renderer.py:305-314) + ray_marcher + :329-330
     cur = {}
     saved = gg.install_contract_hooks(cur)
-    n_per = int(os.environ.get("DE_GOLDEN_PATHS", "40"))
+    n_per = int(os.environ.get("DE_GOLDEN_PATHS", "64"))  # the committed fixture holds 64 per view
     for cname, cfg in cfgs.items():
         key = cname.split()[0].lower()
         gg.apply_config(R, cfg)
@@ -84,7 +84,7 @@ def main():
     for name, fn in saved.items():
         setattr(pt, name, fn)
     G["prev_seed"] = np.uint32(5)
-    outp = os.path.join(HERE, "golden_preview_v1.npz")
+    outp = os.environ.get("DE_GOLDEN_PREVIEW_OUT") or os.path.join(HERE, "golden_preview_v1.npz")
     np.savez_compressed(outp, **G)
     print("wrote %s (%d arrays, %.1f kB) in %.1fs" % (outp, len(G), os.path.getsize(outp) / 1e3, time.time() - t_all))
 

@@ -6,7 +6,8 @@ Tolerance (BASELINE.json north_star): 1e-5 relative FP32.  IEEE-only functions (
 must match bit for bit; functions containing exp/log/pow/sin/cos/atan2/asin get REL = 1e-5 with an
 absolute floor of 1e-5 x the magnitude scale of the quantity (libdevice vs glibc differ by ~1 ulp).
 Stochastic sub-paths (tracking, full paths) branch on those ulps, so a small fraction of items may
-take a different branch: >= 97% of the items must agree to 1e-4 and the means must agree.
+take a different branch: >= 97% of the items must agree to 1e-4 and the means must agree (the achieved
+fraction is printed: run with -s).
 """
 import os
 
@@ -174,6 +175,37 @@ def test_resolve_full_frame(env):
     r.tonemapper = 0
 
 
+@pytest.mark.parametrize("mode", ["wavefront", "megakernel", "preview"])
+def test_resolve_of_the_product_modes(env, mode):
+    """The kernel behind fetch_image() in EVERY mode (bench e2e, smoke, CLI use the product modes) against the golden
+    `_render_to_image` output of the reference source and the oracle, at the 1e-5 tonemap tolerance of the north star:
+    OpenDRT (renderer.py:357) and AgX (:356), with and without a camera response curve."""
+    import digital_earth_b200 as de
+    g, torch, orc = env["g"], env["torch"], env["orc"]
+    tex = {k: g["tex_" + k] for k in orc.TEX_SLOTS}
+    W, H = int(g["img_res"][0]), int(g["img_res"][1])
+    sc = g["cfg_apollo_scalars"]
+    cfg = dict(cam_pos=g["cfg_apollo_cam_pos"], look_at=g["cfg_apollo_look_at"], up=g["cfg_apollo_up"], fov=sc[0], aspect_scale=sc[1], exposure=sc[2],
+               selected_crf=int(sc[3]), gamma=sc[4], sun_angle=sc[5], sun_path_rot=sc[6])
+    r = de.Renderer((W, H), (0, 1, 0), textures=tex, mode=mode)
+    r.apply_config(cfg)
+    acc = torch.as_tensor(g["resolve_accum"], device=r.device)
+    img = r.fetch_image(accum=acc, spp=int(g["resolve_samples"])).permute(1, 0, 2).cpu().numpy()
+    close(img, g["resolve_out"], floor=1e-2, what="_render_to_image, mode=%s vs golden" % mode)
+    for tm, crf, gamma, spp in ((1, int(sc[3]), sc[4], 13), (0, 0, 1.0, 7), (1, 5, 2.2, 3)):
+        r.tonemapper = tm; r.set_crf(crf); r.set_gamma(gamma)
+        s = orc.Scene(tex, W, H, **dict(cfg, selected_crf=crf, gamma=gamma, tonemapper=tm))
+        img = r.fetch_image(accum=acc, spp=spp).permute(1, 0, 2).cpu().numpy()
+        close(img, orc.resolve(s, g["resolve_accum"], spp), floor=1e-2, what="resolve vs oracle, mode=%s tonemapper=%d crf=%d" % (mode, tm, crf))
+    # the accumulation buffer the integrator itself wrote goes through the same kernel
+    r.tonemapper = 0; r.set_crf(int(sc[3])); r.set_gamma(sc[4])
+    r.reset_framebuffer(); r.accumulate(4)
+    s = orc.Scene(tex, W, H, **cfg)
+    img = r.fetch_image().permute(1, 0, 2).cpu().numpy()
+    close(img, orc.resolve(s, r.color_buffer.cpu().numpy(), 4), floor=1e-2, what="resolve of a rendered frame, mode=%s" % mode)
+    r.close()
+
+
 def test_geometry(env):
     g, h = env["g"], env["h"]
     env["scene"]("florida")
@@ -199,19 +231,31 @@ def test_fixed_ray_optical_depth(env):
     close(h.raymarch_T(p, d.astype(np.float32), ext), env["orc"].raymarch_T(p, d.astype(np.float32), ext), floor=1e-2, what="raymarch vs oracle")
 
 
-def _agree(got, want, frac=0.97, rel=1e-4):
+def _agree(got, want, frac=0.97, rel=1e-4, what=""):
     sc = np.maximum(np.abs(want), np.abs(want).max() * 1e-6)
     ok = (np.abs(got - want) <= rel * sc) | (got == want)
     ok = ok.all(axis=1) if ok.ndim > 1 else ok
-    assert ok.mean() >= frac, "only %.1f%% of items agree" % (100 * ok.mean())
+    print("[agree] %s: %d / %d items within %.0e (%.2f%%), required %.0f%%" % (what, ok.sum(), ok.size, rel, 100 * ok.mean(), 100 * frac))
+    assert ok.mean() >= frac, "%s: only %.1f%% of items agree" % (what, 100 * ok.mean())
     return ok
 
 
 def test_tracking(env):
     g, h = env["g"], env["h"]
     env["scene"]()
-    _agree(h.tracking(0, g["trk_pos"], g["trk_dir"], g["trk_land"], g["trk_wl"], int(g["trk_seed"])), g["trk_interaction_out"], frac=0.9)
-    _agree(h.tracking(1, g["trk_pos"], g["trk_dir"], g["trk_land"], g["trk_wl"], int(g["trk_seed"])), g["trk_transmittance_out"], frac=0.9)
+    _agree(h.tracking(0, g["trk_pos"], g["trk_dir"], g["trk_land"], g["trk_wl"], int(g["trk_seed"])), g["trk_interaction_out"], what="sample_interaction vs golden")
+    _agree(h.tracking(1, g["trk_pos"], g["trk_dir"], g["trk_land"], g["trk_wl"], int(g["trk_seed"])), g["trk_transmittance_out"], what="sample_transmittance vs golden")
+    # the same sub-paths on 4096 fresh rays against the oracle (the golden set has 64)
+    rng = np.random.default_rng(17)
+    n = 4096
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p = rng.normal(size=(n, 3)); p /= np.linalg.norm(p, axis=1, keepdims=True)
+    p = (p * (6371e3 + 100.0 + rng.random((n, 1)) * 3e4)).astype(np.float32)
+    land = np.full(n, -1.0, np.float32)
+    wl = (400.0 + 300.0 * rng.random(n)).astype(np.float32)
+    s = env["scene"]()
+    for kind, name in ((0, "sample_interaction"), (1, "sample_transmittance")):
+        _agree(h.tracking(kind, p, d.astype(np.float32), land, wl, 5), env["orc"].tracking(kind, s, p, d.astype(np.float32), land, wl, 5), what=name + " vs oracle, 4096 rays")
 
 
 @pytest.mark.parametrize("key", ["apollo", "florida", "sunset"])
@@ -221,7 +265,11 @@ def test_full_paths_vs_golden(env, key):
     got = h.trace_paths(g["path_%s_px" % key], g["path_%s_py" % key], g["path_%s_sample" % key], int(g["path_seed"]))
     want = g["path_%s_out" % key]
     assert (got[:, 3] == want[:, 3]).all()  # same wavelength for every path
-    _agree(got, want, frac=0.9)
+    ok = _agree(got, want, what="full paths vs golden (%s)" % key)
+    # the few paths that took another branch on an ulp are still samples of the same estimator: means agree
+    m_got, m_want = got[:, 4].mean(), want[:, 4].mean()
+    assert abs(m_got - m_want) <= 0.05 * abs(m_want) + 1e-9, (m_got, m_want, ok.mean())
+    assert np.abs(got[ok, 4] - want[ok, 4]).sum() <= 1e-4 * np.abs(want[ok, 4]).sum() + 1e-12
 
 
 @pytest.mark.parametrize("key", ["apollo", "florida", "sunset"])
@@ -234,7 +282,7 @@ def test_parity_render_vs_oracle_render(env, key):
     r.accumulate(4)
     got = r.color_buffer.cpu().numpy()
     want, _ = orc.render(s, 4, seed=r.seed)
-    px_ok = _agree(got.reshape(-1, 3), want.reshape(-1, 3), frac=0.9, rel=1e-3)
+    px_ok = _agree(got.reshape(-1, 3), want.reshape(-1, 3), frac=0.97, rel=1e-3, what="parity frame vs oracle frame (%s), pixels" % key)
     m_got, m_want = got.mean(), want.mean()
     assert abs(m_got - m_want) <= 0.02 * abs(m_want) + 1e-9, (m_got, m_want, px_ok.mean())
 
@@ -254,7 +302,7 @@ def test_preview_samples_vs_golden(env, golden_preview, key):
     got = h.trace_preview(gp["prev_%s_px" % key], gp["prev_%s_py" % key], gp["prev_%s_sample" % key], int(gp["prev_seed"]))
     want = gp["prev_%s_out" % key]
     assert (got[:, 3] == want[:, 3]).all()
-    _agree(got, want, frac=0.95)
+    _agree(got, want, frac=0.97, what="preview samples vs golden (%s)" % key)
 
 
 def test_preview_mode_frame_vs_oracle(env):

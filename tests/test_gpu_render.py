@@ -330,3 +330,132 @@ def test_more_than_2_to_the_32_paths_in_one_call(de, tex):
     lit = whole.sum(dim=-1) > 0
     assert bool((lit == (halves.sum(dim=-1) > 0)).all())  # the same pixels received light
     r.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Image gates at BASELINE.json sizes: the PRODUCT integrator against the CPU ORACLE, with per-pixel second
+# moments on both sides (de_set_option "moments" / orc.render(second_moment=True)).
+def _var_of_mean(acc, acc2, n):
+    mu = acc / n
+    return mu, np.maximum(acc2 / n - mu * mu, 0.0) / max(n - 1, 1)
+
+
+def _boxes(a, b):
+    h, w = a.shape[:2]
+    return a.reshape(h // b, b, w // b, b, 3).mean((1, 3))
+
+
+def _gpu_render_with_moments(de, tex, scene, w, h, spp, seed, mode="wavefront"):
+    r = make(de, tex, scene, mode, w, h)
+    r.set_option("moments", 1)
+    r.seed = seed
+    r.reset_framebuffer(); r.accumulate(spp)
+    acc, acc2 = r.color_buffer.cpu().numpy().astype(np.float64), r.moment2.cpu().numpy().astype(np.float64)
+    r.close()
+    return acc, acc2
+
+
+def test_second_moment_buffer_matches_the_oracle(de, tex):
+    """Parity flavour and oracle trace the same paths (same Philox keys), so sums AND sums of squares agree pixel by pixel; the
+    product flavours fill the same buffer (Cauchy-Schwarz holds, space-tile kernel included)."""
+    orc, s = oracle_scene(de, tex, "florida")
+    spp = 8
+    acc_o, acc2_o, _ = orc.render(s, spp, seed=5, second_moment=True)
+    acc_g, acc2_g = _gpu_render_with_moments(de, tex, "florida", W, H, spp, 5, mode="parity")
+    assert pixel_agreement(acc_g, acc_o, rel=1e-3) > 0.97 and pixel_agreement(acc2_g, acc2_o, rel=2e-3) > 0.97
+    for scene in ("Apollo 11", "florida"):
+        for mode in ("wavefront", "megakernel"):
+            a, a2 = _gpu_render_with_moments(de, tex, scene, W, H, spp, 5, mode=mode)
+            assert (a2 * spp >= a * a * (1 - 1e-4) - 1e-12).all() and a2.sum() > 0
+
+
+def test_space_tile_kernel_renders_the_same_samples(de, tex):
+    """Tiles whose jittered primary rays all miss the atmosphere shell are rendered by k_space_tiles (no path state, no queues);
+    they must be the same samples with the same values as the generic route: identical up to float summation order, and the
+    classification must never claim a tile that the generic route gives a medium interaction."""
+    w, h = 512, 256
+    out = {}
+    for on in (1, 0):
+        r = make(de, tex, "Apollo 11", "wavefront", w, h)
+        r.set_option("space_tiles", on)
+        r.set_option("timeline", 1)
+        r.set_counting(True)
+        r.reset_framebuffer(); r.accumulate(16)
+        out[on] = (r.color_buffer.cpu().numpy().copy(), r.launch_timeline(), r.counters())
+        r.close()
+    (a1, t1, c1), (a0, t0, c0) = out[1], out[0]
+    n_tiles = (w // 16) * (h // 8)
+    assert t0["space_tiles"] == 0 and t0["wavefront_tiles"] == n_tiles
+    assert t1["space_tiles"] + t1["wavefront_tiles"] == n_tiles and t1["space_tiles"] > 0.4 * n_tiles, t1   # Apollo: the disc fills ~37 % of the frame
+    assert c1["paths"] == c0["paths"] == w * h * 16 and c1["segments"] == c0["segments"] and c1["tex_fetches"] == c0["tex_fetches"]
+    assert np.abs(a1 - a0).max() <= 1e-5 * np.abs(a0).max()
+    assert ((a1 != 0).any(-1) == (a0 != 0).any(-1)).all()
+    # the other two shipped views look at the limb from low orbit: few or no space tiles, still identical
+    for scene in ("florida", "sunset hurricane"):
+        res = []
+        for on in (1, 0):
+            r = make(de, tex, scene, "wavefront", w, h)
+            r.set_option("space_tiles", on)
+            r.reset_framebuffer(); r.accumulate(4)
+            res.append(r.color_buffer.cpu().numpy().copy())
+            r.close()
+        sc = np.maximum(np.abs(res[1]), np.abs(res[1]).max() * 1e-5)
+        assert ((np.abs(res[0] - res[1]) <= 1e-4 * sc).all(-1)).mean() > 0.999   # atomics order only
+
+
+def test_c1_florida_640x360_64spp_wavefront_vs_oracle(de):
+    """BASELINE.json configs[0] at its named size: `config - florida.txt`, 640x360, 64 spp, synthetic 2048x1024 textures.
+    Product integrator (seed A) against the oracle (seed B): box z-test with BOTH renders' own per-pixel second moments, a
+    per-pixel z-test, and the mean radiance within 1 %."""
+    Wc, Hc, spp = 640, 360, 64
+    tex_c1 = de.textures.synthetic(2048, 1024, cloud_cover=0.5, hurricane=False, seed=0)     # bench.py's textures for this view
+    orc, s = oracle_scene(de, tex_c1, "florida", Wc, Hc)
+    acc_o, acc2_o, _ = orc.render(s, spp, seed=12345, second_moment=True)
+    acc_g, acc2_g = _gpu_render_with_moments(de, tex_c1, "florida", Wc, Hc, spp, 777)
+    mu_o, v_o = _var_of_mean(acc_o.astype(np.float64), acc2_o.astype(np.float64), spp)
+    mu_g, v_g = _var_of_mean(acc_g, acc2_g, spp)
+    assert abs(mu_g.mean() - mu_o.mean()) < 0.01 * mu_o.mean(), (mu_g.mean(), mu_o.mean())
+    b = 8
+    bo, bg = _boxes(mu_o, b), _boxes(mu_g, b)
+    vb = (_boxes(v_o, b) + _boxes(v_g, b)) / (b * b)
+    lit = bo.sum(-1) > 1e-4
+    z = ((bg - bo) / np.sqrt(vb + 1e-16))[lit]
+    zp = ((mu_g - mu_o) / np.sqrt(v_o + v_g + 1e-16))[(mu_o.sum(-1) > 1e-4) & (mu_g.sum(-1) > 1e-4)]
+    rel_rmse = np.sqrt(np.mean((bo - bg) ** 2)) / np.mean(bo)
+    noise = np.sqrt(np.mean(vb)) / np.mean(bo)
+    print("[C1] mean %.6g vs oracle %.6g (%.3f%%); 8x8 boxes: mean z %.3f, std z %.3f, |z|>4: %.3f%%; pixels: mean z %.3f, |z|>5: %.3f%%; relRMSE %.4f (noise %.4f)"
+          % (mu_g.mean(), mu_o.mean(), 100 * (mu_g.mean() / mu_o.mean() - 1), z.mean(), z.std(), 100 * np.mean(np.abs(z) > 4), zp.mean(), 100 * np.mean(np.abs(zp) > 5), rel_rmse, noise))
+    assert abs(z.mean()) < 0.15, z.mean()                      # no systematic bias (1e4 boxes: sigma of the mean z ~ 0.01-0.02)
+    assert 0.7 < z.std() < 2.0, z.std()                         # the two renders' own variances explain the differences
+    assert np.mean(np.abs(z) > 4.0) < 0.01, np.mean(np.abs(z) > 4.0)
+    assert abs(zp.mean()) < 0.1 and np.mean(np.abs(zp) > 5.0) < 0.01, (zp.mean(), np.mean(np.abs(zp) > 5.0))
+    assert rel_rmse < 1.3 * noise + 0.005, (rel_rmse, noise)
+
+
+@pytest.mark.parametrize("scene", ["Apollo 11", "florida", "sunset hurricane"])
+def test_4096spp_rel_rmse_wavefront_vs_oracle(de, tex, scene):
+    """North-star image gate against the ORACLE: relative RMSE < 1 % at 4096 spp on the linear accumulation buffer (128x64 frame,
+    independent seeds; 32x32 boxes, where the residual Monte-Carlo noise of both 4096-spp renders is below the gate), mean
+    radiance within 0.5 %, box z-test from both renders' second moments."""
+    spp = 4096
+    orc, s = oracle_scene(de, tex, scene)
+    acc_o, acc2_o, _ = orc.render(s, spp, seed=4242, second_moment=True)
+    acc_g, acc2_g = _gpu_render_with_moments(de, tex, scene, W, H, spp, 1717)
+    mu_o, v_o = _var_of_mean(acc_o.astype(np.float64), acc2_o.astype(np.float64), spp)
+    mu_g, v_g = _var_of_mean(acc_g, acc2_g, spp)
+    big_o, big_g = _boxes(mu_o, 32), _boxes(mu_g, 32)
+    rel_rmse_big = np.sqrt(np.mean((big_o - big_g) ** 2)) / np.mean(big_o)
+    noise_big = np.sqrt(np.mean((_boxes(v_o, 32) + _boxes(v_g, 32)) / 1024.0)) / np.mean(big_o)
+    bo, bg = _boxes(mu_o, 8), _boxes(mu_g, 8)
+    vb = (_boxes(v_o, 8) + _boxes(v_g, 8)) / 64.0
+    rel_rmse = np.sqrt(np.mean((bo - bg) ** 2)) / np.mean(bo)
+    noise = np.sqrt(np.mean(vb)) / np.mean(bo)
+    lit = bo.sum(-1) > 1e-4
+    z = ((bg - bo) / np.sqrt(vb + 1e-16))[lit]
+    print("[4096 spp, %s] mean %.6g vs oracle %.6g (%+.3f%%); relRMSE 32x32 boxes %.4f%% (noise %.4f%%), 8x8 boxes %.4f%% (noise %.4f%%); z: mean %.3f std %.3f, |z|>4: %.2f%%"
+          % (scene, mu_g.mean(), mu_o.mean(), 100 * (mu_g.mean() / mu_o.mean() - 1), 100 * rel_rmse_big, 100 * noise_big, 100 * rel_rmse, 100 * noise, z.mean(), z.std(),
+             100 * np.mean(np.abs(z) > 4)))
+    assert abs(mu_g.mean() - mu_o.mean()) < 0.005 * mu_o.mean(), (mu_g.mean(), mu_o.mean())
+    assert rel_rmse_big < 0.01, (rel_rmse_big, noise_big)       # the 1 % gate
+    assert rel_rmse < 1.3 * noise + 0.002, (rel_rmse, noise)
+    assert abs(z.mean()) < 0.35 and np.mean(np.abs(z) > 4.0) < 0.02, (z.mean(), np.mean(np.abs(z) > 4.0))

@@ -71,6 +71,11 @@ def rsi(o, d, r):
     return -b - s, -b + s
 
 
+def pos_noise(o, tm):
+    """de_device.cuh pos_noise: bound on |fl(o + d t) - (o + d t)| for t <= tm"""
+    return 3e-7 * (abs(o[0]) + abs(o[1]) + abs(o[2]) + tm)
+
+
 def cloud_limits(o, d, land):
     return orc.cloud_limits(o[None].astype(F), d[None].astype(F), np.array([land], F))[0]
 
@@ -125,8 +130,9 @@ def test_cloud_majorant_and_layer_top_are_exact_bounds(cloud_scene):
         if cmax == 0.0:
             assert dens.max() == 0.0                                                 # the pass is skipped
         elif cmax < 0.99:                                                            # cloud_pass_setup: cut at the layer top
-            top = rsi(o[i], d[i], LOWER + THICK * (0.2 + 0.8 * cmax + 1e-3))
-            ts2, tm2 = (ts, ts) if top is None else (max(ts, top[0]), min(tm, top[1]))
+            margin = 1e-3 + pos_noise(o[i], tm) / THICK                              # grows with the camera distance (f32 positions)
+            top = rsi(o[i] + d[i] * ts, d[i], LOWER + THICK * (0.2 + 0.8 * cmax + margin))   # intersected from the pass's entry point
+            ts2, tm2 = (ts, ts) if top is None else (max(ts, ts + top[0]), min(tm, ts + top[1]))
             outside = (t < ts2) | (t > tm2)
             cut += int(outside.any())
             assert dens[outside].max(initial=0.0) == 0.0, (i, cmax)                   # nothing but null collisions was removed
@@ -151,10 +157,11 @@ def test_rmo_majorant_bounds_every_point_of_the_segment():
             tm = min(tm, land[0])
         if not ts < tm:
             continue
-        # rmo_segment_majorant: densities at the LOWEST point of the segment (perigee clamped to it)
-        bdot, r2 = float(np.dot(o[i], d[i])), float(np.dot(o[i], o[i]))
-        tp = min(max(-bdot, ts), tm)
-        hmin = max(np.sqrt(max(r2 + tp * (2 * bdot + tp), 0.0)) - R - 2.0, 0.0)
+        # rmo_segment_majorant: densities at the LOWEST point of the segment (perigee clamped to it), from the entry point
+        p = o[i] + d[i] * ts
+        bdot, r2 = float(np.dot(p, d[i])), float(np.dot(p, p))
+        tp = min(max(-bdot, 0.0), tm - ts)
+        hmin = max(np.sqrt(max(r2 + tp * (2 * bdot + tp), 0.0)) - R - (2.0 + pos_noise(o[i], tm)), 0.0)
         dl = orc.density(np.array([hmin], F))[0].astype(np.float64)
         oz = 1.0 if hmin < 25000.0 else dl[2]
         ext = ext_all[wl[i]]
@@ -165,6 +172,59 @@ def test_rmo_majorant_bounds_every_point_of_the_segment():
         sig = dens @ ext
         bad += int(sig.max() > maj * (1 + 2e-6))
     assert bad == 0
+
+
+def test_rmo_majorant_in_float32_from_the_apollo_camera():
+    """primary rays of the headline view start 5.7e7 m from the planet centre, where o.o ~ 3e15 has an ulp of 2.7e8 --
+    a perigee evaluated from the ray ORIGIN in f32 came out up to ~70 m too high and the 'exact' majorant dipped below sigma.rho near
+    the ray's lowest point.  Restated here in float32 operation by operation (as csrc/de_device.cuh now computes it: from the
+    segment's entry point, slack growing with the camera distance) against the oracle's densities at the f32 positions fl(o + d t)
+    the tracking loop evaluates; the old formula is replayed too and must show the defect this test exists to catch."""
+    import os
+    cfg = de.load_config(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "digital-earth_b200", "assets", "configs", "config - Apollo 11.txt"))
+    s = orc.Scene(de.textures.synthetic(64, 32, seed=1), 1920, 1080, cam_pos=cfg["cam_pos"], look_at=cfg["look_at"], up=cfg["up"], fov=cfg["fov"],
+                  aspect_scale=cfg["aspect_scale"], sun_angle=cfg["sun_angle"], sun_path_rot=cfg["sun_path_rot"])
+    rng = np.random.default_rng(21)
+    n = 60000
+    u, v = rng.integers(0, 1920, n).astype(F), rng.integers(0, 1080, n).astype(F)
+    d = orc.cast_dir(s, u, v, rng.integers(0, 2 ** 32, (n, 2), dtype=np.uint64).astype(np.uint32))
+    o = np.tile(np.asarray(cfg["cam_pos"], F), (n, 1))
+    atm, gnd = orc.rsi(o, d, np.full(n, ATM, F)), orc.rsi(o, d, np.full(n, R, F))
+    ts = np.maximum(atm[:, 0], F(0))
+    tm = np.where(gnd[:, 0] > 0, gnd[:, 0], atm[:, 1]).astype(F)
+    keep = ts < tm
+    o, d, ts, tm = o[keep], d[keep], ts[keep], tm[keep]
+    assert len(ts) > 0.3 * n
+    dot = lambda a, b: ((a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1]).astype(F) + a[:, 2] * b[:, 2]).astype(F)  # noqa: E731  (de_device.cuh dot)
+    ext = orc.spectra(np.array([450.0], F))[0, :3].astype(F)
+
+    def majorant(hmin):
+        dl = orc.density(np.maximum(hmin, F(0)).astype(F))
+        oz = np.where(hmin < 25000.0, F(1.0), dl[:, 2])
+        return (F(1.001) * (ext[0] * dl[:, 0] + ext[1] * dl[:, 1]) + ext[2] * oz).astype(F)
+
+    # new: from the entry point
+    p = (o + d * ts[:, None]).astype(F)
+    b, r2 = dot(p, d), dot(p, p)
+    tp = np.minimum(np.maximum(-b, F(0)), tm - ts).astype(F)
+    slack = (F(2.0) + F(3e-7) * (np.abs(o).sum(1, dtype=F) + tm)).astype(F)
+    hmin_new = np.maximum(np.sqrt(np.maximum(r2 + tp * (F(2.0) * b + tp), F(0))).astype(F) - F(R) - slack, F(0)).astype(F)
+    # old: from the origin
+    b0, r20 = dot(o, d), dot(o, o)
+    tp0 = np.minimum(np.maximum(-b0, ts), tm).astype(F)
+    hmin_old = np.maximum(np.sqrt(np.maximum(r20 + tp0 * (F(2.0) * b0 + tp0), F(0))).astype(F) - F(R) - F(2.0), F(0)).astype(F)
+    # truth: the lowest f32 position the loop can evaluate, on a dense parameter grid around the perigee
+    b64 = np.einsum("ij,ij->i", o.astype(np.float64), d.astype(np.float64))
+    tper = np.clip(-b64, ts, tm)
+    k = np.linspace(-1.0, 1.0, 41)
+    t = np.clip(tper[:, None] + k[None, :] * 3.0e4, ts[:, None], tm[:, None]).astype(F)
+    pos = (o[:, None, :] + d[:, None, :] * t[:, :, None]).astype(F)
+    h_true = (np.sqrt((pos.astype(np.float64) ** 2).sum(-1)) - R).min(1)
+    sig_true = (orc.density(np.maximum(h_true, 0).astype(F)) * ext[None, :]).sum(1)
+    assert (sig_true <= majorant(hmin_new) * (1 + 1e-6)).all(), "f32 majorant from the entry point fails at the Apollo camera distance"
+    assert (hmin_new <= np.maximum(h_true, 0.0) + 1e-3).all()   # (rays that end on the sea-level sphere sit at h = 0 +- f32 noise)
+    assert (hmin_old > h_true + 5.0).mean() > 0.05, "the old (origin-based) perigee no longer shows the cancellation this test documents"
+    assert (np.maximum(h_true, 0.0) - hmin_new).max() < 120.0                 # ... and the price is small: the bound sits < 120 m below the true perigee
 
 
 def test_land_surely_missed_never_discards_a_hit():
