@@ -19,6 +19,8 @@ frame = W*H*spp path samples through the product (wavefront) integrator.
 N > 1: the frame's samples are sliced across ranks (rank r renders sample indices [r*spp/N, (r+1)*spp/N)
 of every pixel: perfectly balanced, the union is the 1-GPU sample set) and the float accumulation
 buffers are sum-reduced to rank 0 with NCCL inside the timed region; total work is fixed -> "strong".
+--partition tile / tile+spp splits by interleaved 16x8 film tiles (x sample slices) instead; after the timed
+region rank 0 re-renders a 64x32 crop alone and the line carries the N-GPU == 1-GPU difference ("identity").
 --impl reference: the reference itself needs Taichi (absent); its CPU implementation is therefore the
 oracle port, timed on all host threads on the bounded sample per step.
 """
@@ -54,7 +56,31 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "fused"],
                     help="N>1: ncclReduce of the accumulation buffers, or rank 0's resolve kernel reading the peers' buffers over NVLink P2P")
+    ap.add_argument("--partition", default="spp", choices=["spp", "tile", "tile+spp"],
+                    help="N>1: sample slices, interleaved 16x8 film tiles, or tile groups x sample slices (SURVEY 8e)")
+    ap.add_argument("--tile-groups", type=int, default=0, help="tile+spp: number of tile groups (default 2)")
+    ap.add_argument("--no-identity", action="store_true", help="N>1: skip the N-GPU == 1-GPU check of a 64x32 crop after the timed region")
     return ap.parse_args()
+
+
+def tile_groups_of(a, world):
+    if a.partition == "spp" or world == 1:
+        return 1
+    if a.partition == "tile":
+        return world
+    g = a.tile_groups or 2
+    if world % g:
+        raise SystemExit("--tile-groups %d does not divide %d ranks" % (g, world))
+    return g
+
+
+def ncu_metrics(a):
+    """issue / pipe / lane figures of the render kernel are hardware counters: they come from the committed ncu capture of this
+    view (profiles/r2_ncu_metrics.json, written by tools/ncu_metrics_json.py from the .ncu-rep), never from a run under a profiler."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_metrics.json"))).get(a.scene)
+    except Exception:
+        return None
 
 
 def flop_per_path(c):
@@ -175,8 +201,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W, H = map(int, a.res.split("x"))
     tw, th = map(int, a.tex.split("x"))
-    from digital_earth_b200.distributed import sample_slice, reduce_accumulation
-    first, spp_local = sample_slice(a.spp, rank, world)
+    from digital_earth_b200.distributed import partition, reduce_accumulation, render_partition
+    groups = tile_groups_of(a, world)
+    part = partition(a.spp, rank, world, groups)
+    first, spp_local = part["first_sample"], part["n_spp"]
+    tiles = (part["tile_stride"], part["tile_offset"]) if groups > 1 else None
 
     tex = textures_for(a, tw, th)
     cfg = scene_cfg(a)
@@ -192,18 +221,18 @@ def main():
         dist.all_gather_object(handles, r.export_accum_handle())
         if rank == 0:
             peers = [r.open_peer(handles[k]) for k in range(1, world)]
+    peer_offsets = [k % groups for k in range(1, world)]
 
     def step(e2e):
         flush.fill_(1)  # evict L2 between timed iterations (textures alone are 416 MB > L2 as well)
         if e2e:
             r.apply_config(cfg)   # host -> device: scene parameters for this frame
-        r.reset_framebuffer()
-        r.accumulate(spp_local, first_sample=first)
+        render_partition(r, part)  # reset + this rank's (tile group, sample slice)
         if fused:
             # exchange fused into the resolve: a 4-byte all-reduce is the stream-ordered "all ranks have rendered" barrier,
             # rank 0's resolve kernel then sums the peers' buffers in place, a second token releases the buffers
             dist.all_reduce(token)
-            img = r.fetch_image_peers(peers, a.spp) if rank == 0 else None
+            img = r.fetch_image_peers(peers, a.spp, tile_stride=groups, own_offset=0, peer_offsets=peer_offsets) if rank == 0 else None
             dist.all_reduce(token)
         else:
             reduce_accumulation(r.color_buffer, dst=0)  # ncclReduce(sum) over NVLink: the path's one exchange step (no-op at N=1)
@@ -230,9 +259,10 @@ def main():
 
     # event counters -> algorithmic FLOP/path (outside the timed region, reduced spp)
     r.set_counting(True)
-    r.reset_framebuffer(); r.accumulate(4, first_sample=first)
+    r.reset_framebuffer(); r.accumulate(4, first_sample=first, tiles=tiles)
     counters = r.counters()
     r.set_counting(False)
+    tex_peak = r.tex_gather_peak() if rank == 0 else None   # measured rate of the fetch instruction the kernel uses (outside the timed region)
 
     for _ in range(max(a.warmup, 0)):
         step(False)
@@ -244,11 +274,39 @@ def main():
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     r.reset_framebuffer()
-    k0.record(); r.accumulate(spp_local, first_sample=first); k1.record()
+    k0.record(); r.accumulate(spp_local, first_sample=first, tiles=tiles); k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1)
     step(True)
     ms_e2e = timed(True, a.steps)
+
+    # the reference's only shipped mode is ONE sample per displayed frame (earth_viewer.py:186,241-243): accumulate() + fetch_image(),
+    # measured as such on this GPU (median of 9, warm L2 -- consecutive frames of a progressive render)
+    one = []
+    r.reset_framebuffer()
+    for _ in range(12):
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(); r.accumulate(1); r.fetch_image(); f1.record()
+        torch.cuda.synchronize()
+        one.append(f0.elapsed_time(f1))
+    ms_1spp = sorted(one[3:])[len(one[3:]) // 2]
+
+    # N-GPU == 1-GPU (SURVEY 8e determinism check): the reduced frame of one more partitioned render against rank 0 rendering a
+    # 64x32 crop of it alone with the same (pixel, sample) keys; equal up to float summation order
+    identity = None
+    if world > 1 and not a.no_identity:
+        render_partition(r, part)
+        reduce_accumulation(r.color_buffer, dst=0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            cx, cy = (W // 2 - 32) // 16 * 16, (H // 2 - 16) // 8 * 8
+            multi = r.color_buffer[cy:cy + 32, cx:cx + 64].clone()
+            r.reset_framebuffer(); r.accumulate(a.spp, window=(cx, cy, 64, 32), first_sample=0)
+            single = r.color_buffer[cy:cy + 32, cx:cx + 64]
+            den = float(single.abs().max())
+            identity = {"crop": [cx, cy, 64, 32], "max_abs_diff_over_max": float((multi - single).abs().max()) / max(den, 1e-30),
+                        "rel_diff_of_mean": abs(float(multi.mean()) - float(single.mean())) / max(abs(float(single.mean())), 1e-30)}
+        dist.barrier()
 
     paths_step = W * H * a.spp
     value = paths_step * a.steps / (ms * 1e-3)
@@ -271,7 +329,12 @@ def main():
             ocnt, events_src = counters, "KERNEL counters (no oracle fixture for this view): lower bound of the reference's work"
         fpp = flop_per_path(ocnt)
         peak_tflops = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # FP32 FMA issue peak
-        achieved = fpp * (W * H * spp_local) / (kernel_ms * 1e-3) / 1e12
+        paths_launch = W * H * spp_local / groups                   # paths of this rank's launch (tile groups render 1/groups of the film)
+        achieved = fpp * paths_launch / (kernel_ms * 1e-3) / 1e12
+        executed = flop_per_path(counters) * paths_launch / (kernel_ms * 1e-3) / 1e12
+        kpp = {k: counters[k] / max(counters["paths"], 1) for k in ("segments", "rmo_steps", "cloud_steps", "sdf_evals", "tex_fetches", "surface_hits")}
+        fetch_rate = kpp["tex_fetches"] * paths_launch / (kernel_ms * 1e-3)   # 2x2 footprints per second (one gather each for r8 maps)
+        hw = ncu_metrics(a) or {}
         traffic = None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -283,19 +346,33 @@ def main():
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s (config - %s.txt), %dx%d, %d spp, synthetic %dx%d textures" % (a.scene, SCENES[a.scene], W, H, a.spp, tw, th),
                        "scene": a.scene, "integrator": a.mode, "ms_per_frame": ms / a.steps, "ms_per_spp": ms / a.steps / a.spp,
-                       "partition": ("spp-slice x%d + %s" % (world, "resolve kernel summing the peers' f32 accumulation buffers over NVLink P2P (CUDA IPC)" if fused
-                                                             else "ncclReduce(sum) of the f32 accumulation buffer")) if world > 1 else "single GPU",
+                       "ms_1spp": ms_1spp,
+                       "ms_1spp_note": "measured: one accumulate(1) + fetch_image() per frame (the reference's interactive mode), median of 9; ms_per_spp is the amortised figure",
+                       "partition": ("%s + %s" % ("spp-slice x%d" % world if groups == 1 else ("interleaved 16x8 film tiles x%d" % world if groups == world else
+                                                  "%d tile groups x %d spp slices" % (groups, world // groups)),
+                                                  "resolve kernel reading the peers' f32 accumulation buffers over NVLink P2P (CUDA IPC)" if fused
+                                                  else "ncclReduce(sum) of the f32 accumulation buffer")) if world > 1 else "single GPU",
                        "l2": "256 MiB flush between steps; textures (416 MB) exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": 96, "d2h_bytes_per_step": W * H * 3 * 4},
-            "gpu_launches": a.steps * (2 if fused else 1),  # k_render_wavefront (+ k_resolve_peers with --exchange fused) per step; memsets and NCCL are not ours
+            "gpu_launches": a.steps * (3 if fused else 2),  # k_render_wavefront + k_space_tiles (+ k_resolve_peers with --exchange fused) per step; memsets and NCCL are not ours
             "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                          "traffic": traffic, "kernel": "k_render_wavefront", "kernel_ms": kernel_ms, "flop_per_path": fpp,
                          "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (max SM clock of MEASURED_PEAKS.json); HBM/tensor peaks do not bound this path" % sm_max,
                          "flop_model": "60*N_rmo+45*N_cloud+45*N_sdf+400*N_seg+200 (SURVEY 8d); N from " + events_src,
                          "oracle_events_per_path": {k: ocnt[k] / max(ocnt["paths"], 1) for k in ("segments", "rmo_steps", "cloud_steps", "sdf_evals", "tex_fetches", "surface_hits")},
-                         "kernel_events_per_path": {k: counters[k] / max(counters["paths"], 1) for k in ("segments", "rmo_steps", "cloud_steps", "sdf_evals", "tex_fetches", "surface_hits")}},
+                         "kernel_events_per_path": kpp,
+                         "note": "achieved / frac = the REFERENCE algorithm's work (oracle event counts, SURVEY 8d) per second: a reference-equivalent rate. "
+                                 "executed_* = the same FLOP model on the kernel's own counters (local majorants and miss tests remove 2-4x of the steps): hardware utilisation",
+                         "executed_tflops": executed, "executed_frac": executed / peak_tflops,
+                         "tex_fetches_per_s": fetch_rate, "tex_peak_fetches_per_s": tex_peak, "tex_frac": (fetch_rate / tex_peak) if tex_peak else None,
+                         "tex_peak_source": "de_bench_tex_gather: tex2Dgather r8, L1-resident footprints, 2048 threads/SM, measured in this run",
+                         "issue_active_pct": hw.get("issue_active_pct"), "lanes_per_inst": hw.get("lanes_per_inst"), "xu_pct": hw.get("xu_pct"),
+                         "alu_pct": hw.get("alu_pct"), "fma_pct": hw.get("fma_pct"), "l1tex_hit_pct": hw.get("l1tex_hit_pct"), "l2_hit_pct": hw.get("l2_hit_pct"),
+                         "hw_counter_source": hw.get("source")},
             "clocks": clocks,
         }
+        if identity:
+            line["identity"] = identity
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -45,11 +45,15 @@ _SIGS = {
     "de_set_option": ([_P, C.c_char_p, _I], _I),
     "de_get_moment2": ([_P, C.POINTER(_P)], _I),
     "de_get_launch_timeline": ([_P, _P], _I),
+    "de_get_cta_timeline": ([_P, _P, _I], _I),
+    "de_bench_tex_gather": ([_P, _I, _I, C.POINTER(C.c_double)], _I),
     "de_set_params": ([_P, C.POINTER(DeParams)], _I),
     "de_upload_texture": ([_P, _I, _P, _I, _I, _I], _I),
     "de_upload_luts": ([_P, _P, _P, _P, _P, _I], _I),
     "de_reset": ([_P], _I),
     "de_accumulate": ([_P, _I, _U, _U, _I, _I, _I, _I], _I),
+    "de_accumulate_tiles": ([_P, _I, _U, _U, _I, _I], _I),
+    "de_resolve_peers_tiled": ([_P, C.POINTER(_P), C.POINTER(C.c_int), _I, _I, _I, _P, _I], _I),
     "de_get_accum": ([_P, C.POINTER(_P)], _I),
     "de_resolve": ([_P, _P, _P, _I], _I),
     "de_ipc_export_accum": ([_P, _P], _I),
@@ -90,6 +94,7 @@ _SIGS = {
     "de_test_fast_cloud_bound": ([_P, _P, _P, _P, _P, _P, _I], _I),
     "de_test_fast_rmo_majorant": ([_P, _P, _P, _P, _P, _P, _P, _I], _I),
     "de_test_fast_land": ([_P, _P, _P, _P, _I], _I),
+    "de_test_fast_rmo_bands": ([_P, _P, _P, _P, _P, _P, _P, _I, _P, _I], _I),
 }
 EXPORTS = tuple(_SIGS)
 

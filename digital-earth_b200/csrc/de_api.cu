@@ -3,6 +3,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -37,6 +38,38 @@ struct de_ctx {
 };
 
 namespace {
+// Density bounds per altitude band for the product flavour's rmo majorant (de_device.cuh, rmo_band_*): the reference's fits
+// (volume_rendering_models.py:229-273) in double precision at the band's bottom (Rayleigh, aerosol: decreasing with altitude) and the
+// maximum of the ozone fit over the band (it peaks at 25 km), each taken 100 m beyond the band (f32 positions of a far camera are
+// +- 15 m off the ideal ray) and 0.2 % up (MUFU exponentials, the 1.3e-5 step of the aerosol fit at 11.5 km).
+double fit_rayl(double h) { return 3.68082 * std::exp(-(h + 24239.99) * (h + 24239.99) / 532307548.4168) / 1.225; }
+double fit_mie(double h) {
+    double d;
+    if (h > 11500.0) d = 0.0918 * std::exp(-1.0e-6 * (h - 11500.0) * (h - 11500.0));
+    else if (h > 2400.0) d = 0.3000 * std::exp(-2.5e-9 * (h + 2500.0) * (h + 2500.0)) - 0.092;
+    else if (h > 1300.0) d = 0.6500 * std::exp(-5.0e-6 * (h - 1300.0) * (h - 1300.0)) + 0.18899;
+    else d = 1.0 - h / 8136.646;
+    return d * 1.06;
+}
+double fit_ozone(double h) {
+    const double k = h * 0.001, d2 = (k - 25.0) * (k - 25.0);
+    const double c = -0.000015 * (k - 15.0) * (k - 15.0) * (k - 15.0);
+    return 0.625 * std::exp(-d2 / 49.0) + 0.375 * std::exp(-d2 / 256.0) + (c > 0.0 ? c : 0.0);
+}
+void build_rmo_bands(DevScene &s) {
+    const double edge[kDeRmoBands + 1] = {0.0, 4000.0, 12000.0, 30000.0, 110000.0};
+    const double margin = 100.0, up = 1.002;
+    for (int k = 0; k < kDeRmoBands; ++k) {
+        const double lo = edge[k] > margin ? edge[k] - margin : 0.0, hi = edge[k + 1] + margin;
+        s.band_r[k] = (float)(6371000.0 + edge[k]);
+        double m_mie = 0.0, m_oz = 0.0, m_ray = 0.0;
+        for (int j = 0; j <= 4000; ++j) {            // dense scan: no monotonicity assumed
+            const double h = lo + (hi - lo) * j / 4000.0;
+            m_ray = std::fmax(m_ray, fit_rayl(h)); m_mie = std::fmax(m_mie, fit_mie(h)); m_oz = std::fmax(m_oz, fit_ozone(h));
+        }
+        s.band_dr[k] = (float)(m_ray * up); s.band_dm[k] = (float)(m_mie * up); s.band_do[k] = (float)(m_oz * up);
+    }
+}
 int fail(de_ctx *c, int code, const std::string &msg) {
     if (c) c->err = msg;
     return code;
@@ -106,6 +139,7 @@ int de_create(de_ctx **out, int device, int width, int height) {
     de_ctx *ctx = new (std::nothrow) de_ctx();
     if (!ctx) return DE_ERR_NOMEM;
     ctx->device = device; ctx->W = width; ctx->H = height;
+    build_rmo_bands(ctx->scene);
     auto bail = [&](cudaError_t e) { (void)e; de_destroy(ctx); return DE_ERR_CUDA; };
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e);
@@ -216,6 +250,30 @@ int de_get_stage_profile(de_ctx *ctx, uint64_t *out32) {
     for (int k = 0; k < 32; ++k) out32[k] = buf[k];
     return DE_OK;
 }
+int de_get_cta_timeline(de_ctx *ctx, uint64_t *out, int max_ctas) {
+    if (!ctx) return DE_ERR_INVALID;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return DE_ERR_CUDA;
+    if (!out || max_ctas <= 0) return fail(ctx, DE_ERR_INVALID, "out is NULL / max_ctas <= 0");
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(ctx, DE_ERR_CUDA, "sync failed");
+    if (!ctx->wf) return fail(ctx, DE_ERR_STATE, "the wavefront integrator has not run yet");
+    const int n = de_wavefront_cta_stats(ctx->wf, (unsigned long long *)out, max_ctas);
+    return n >= 0 ? n : fail(ctx, DE_ERR_CUDA, "cta timeline copy failed");
+}
+int de_bench_tex_gather(de_ctx *ctx, int slot, int iters, double *gathers_per_second) {
+    ENTER();
+    NEED(slot >= 0 && slot < DE_TEX_COUNT && ctx->have_tex[slot] && ctx->scene.tex[slot].obj, "texture slot not uploaded");
+    NEED(iters > 0 && gathers_per_second, "bad arguments");
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    const int ctas = sms * 8;                                       // 2048 threads per SM: every TEX unit saturated
+    float *scratch = nullptr;
+    CU(cudaMalloc(&scratch, (size_t)ctas * 256 * sizeof(float)));
+    const float ms = de_fast::bench_tex_gather(ctx->scene.tex[slot].obj, ctx->scene.tex[slot].w, ctx->scene.tex[slot].h, ctas, iters, scratch, ctx->stream);
+    cudaFree(scratch);
+    if (!(ms > 0.0f)) return fail(ctx, DE_ERR_CUDA, "tex gather microbenchmark failed");
+    *gathers_per_second = (double)ctas * 256.0 * (double)iters / ((double)ms * 1e-3);
+    return check_launch(ctx, "tex_gather_peak");
+}
 int de_set_counting(de_ctx *ctx, int enabled) {
     ENTER();
     ctx->counting = enabled != 0;
@@ -320,16 +378,16 @@ int de_reset(de_ctx *ctx) {
     return DE_OK;
 }
 
-int de_accumulate(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h) {
-    ENTER();
+static int accumulate_impl(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, int stride, int offset) {
     NEED(n_spp > 0, "n_spp <= 0");
     NEED(x0 >= 0 && y0 >= 0 && w > 0 && h > 0 && x0 + w <= ctx->W && y0 + h <= ctx->H, "window outside the frame");
+    NEED(stride >= 1 && offset >= 0 && offset < stride, "tile partition: need 0 <= offset < stride");
     int rc = ready_to_render(ctx);
     if (rc) return rc;
     float *a2 = ctx->d_accum2;
-    if (ctx->mode == DE_MODE_PARITY) de_exact::launch_render_mega(ctx->scene, ctx->d_accum, a2, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
-    else if (ctx->mode == DE_MODE_PREVIEW) de_fast::launch_render_preview(ctx->scene, ctx->d_accum, a2, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
-    else if (ctx->mode == DE_MODE_MEGAKERNEL) de_fast::launch_render_mega(ctx->scene, ctx->d_accum, a2, n_spp, seed, first_sample, x0, y0, w, h, ctx->counting, ctx->stream);
+    if (ctx->mode == DE_MODE_PARITY) de_exact::launch_render_mega(ctx->scene, ctx->d_accum, a2, n_spp, seed, first_sample, x0, y0, w, h, stride, offset, ctx->counting, ctx->stream);
+    else if (ctx->mode == DE_MODE_PREVIEW) de_fast::launch_render_preview(ctx->scene, ctx->d_accum, a2, n_spp, seed, first_sample, x0, y0, w, h, stride, offset, ctx->counting, ctx->stream);
+    else if (ctx->mode == DE_MODE_MEGAKERNEL) de_fast::launch_render_mega(ctx->scene, ctx->d_accum, a2, n_spp, seed, first_sample, x0, y0, w, h, stride, offset, ctx->counting, ctx->stream);
     else {
         if (!ctx->wf) {
             ctx->wf = de_wavefront_alloc(ctx->device);
@@ -341,9 +399,18 @@ int de_accumulate(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, 
         job.count = ctx->counting; job.timeline = ctx->opt_timeline;
         job.space_tiles = ctx->opt_space_tiles; job.space_async = ctx->opt_space_async;
         job.param_version = ctx->param_version;
+        job.tile_stride = stride; job.tile_offset = offset;
         if (de_wavefront_render(ctx->wf, ctx->scene, job, ctx->stream) != 0) return fail(ctx, DE_ERR_NOMEM, "wavefront tile buffers: allocation failed");
     }
     return check_launch(ctx, "render");
+}
+int de_accumulate(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h) {
+    ENTER();
+    return accumulate_impl(ctx, n_spp, seed, first_sample, x0, y0, w, h, 1, 0);
+}
+int de_accumulate_tiles(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, int tile_stride, int tile_offset) {
+    ENTER();
+    return accumulate_impl(ctx, n_spp, seed, first_sample, 0, 0, ctx->W, ctx->H, tile_stride, tile_offset);
 }
 
 int de_get_accum(de_ctx *ctx, float **dev_ptr) {
@@ -401,18 +468,27 @@ int de_ipc_close_peers(de_ctx *ctx) {
     return rc;
 }
 
-int de_resolve_peers(de_ctx *ctx, const float *const *peer_accums, int n_peers, float *dev_out, int spp_total) {
+int de_resolve_peers_tiled(de_ctx *ctx, const float *const *peer_accums, const int *peer_tile_offsets, int n_peers, int tile_stride, int own_tile_offset,
+                           float *dev_out, int spp_total) {
     ENTER();
     NEED(dev_out, "dev_out is NULL");
     NEED(spp_total > 0, "spp_total <= 0");
     NEED(n_peers >= 0 && n_peers <= kDeMaxPeers, "n_peers out of range (0..15)");
     NEED(n_peers == 0 || peer_accums, "peer_accums is NULL");
-    for (int k = 0; k < n_peers; ++k) NEED(peer_accums[k], "a peer pointer is NULL");
+    NEED(tile_stride >= 1 && own_tile_offset >= 0 && own_tile_offset < tile_stride, "tile partition: need 0 <= offset < stride");
+    NEED(tile_stride == 1 || n_peers == 0 || peer_tile_offsets, "peer_tile_offsets is NULL");
+    for (int k = 0; k < n_peers; ++k) {
+        NEED(peer_accums[k], "a peer pointer is NULL");
+        NEED(tile_stride == 1 || (peer_tile_offsets[k] >= 0 && peer_tile_offsets[k] < tile_stride), "a peer tile offset is out of range");
+    }
     if (!ctx->have_params || !ctx->have_luts) return fail(ctx, DE_ERR_STATE, "params / LUTs missing");
     int rc = refresh_scene(ctx);
     if (rc) return rc;
-    de_exact::launch_resolve_peers(ctx->scene, ctx->d_accum, peer_accums, n_peers, dev_out, spp_total, ctx->stream);
+    de_exact::launch_resolve_peers(ctx->scene, ctx->d_accum, peer_accums, peer_tile_offsets, n_peers, tile_stride, own_tile_offset, dev_out, spp_total, ctx->stream);
     return check_launch(ctx, "resolve_peers");
+}
+int de_resolve_peers(de_ctx *ctx, const float *const *peer_accums, int n_peers, float *dev_out, int spp_total) {
+    return de_resolve_peers_tiled(ctx, peer_accums, nullptr, n_peers, 1, 0, dev_out, spp_total);
 }
 
 int de_fetch_image_host(de_ctx *ctx, float *host_out, int spp_total) {
@@ -495,6 +571,14 @@ int de_test_fast_cloud_bound(de_ctx *ctx, const float *pos, const float *dir, co
 }
 int de_test_fast_rmo_majorant(de_ctx *ctx, const float *pos, const float *dir, const float *ts, const float *tm, const float *ext3, float *out, int n) {
     HOOK_PRE(false); de_fast::t_fast_rmo_majorant(pos, dir, ts, tm, ext3, out, n, ctx->stream); HOOK_POST("fast_rmo_majorant");
+}
+int de_test_fast_rmo_bands(de_ctx *ctx, const float *pos, const float *dir, const float *ts, const float *tm, const float *ext3, const float *t_query, int n_query,
+                           float *out, int n) {
+    HOOK_PRE(false);
+    NEED(n_query > 0 && t_query, "bad query arguments");
+    int rc = refresh_scene(ctx);
+    if (rc) return rc;
+    de_fast::t_fast_rmo_bands(ctx->scene, pos, dir, ts, tm, ext3, t_query, n_query, out, n, ctx->stream); HOOK_POST("fast_rmo_bands");
 }
 int de_test_fast_land(de_ctx *ctx, const float *pos, const float *dir, float *out3, int n) {
     HOOK_PRE(true);

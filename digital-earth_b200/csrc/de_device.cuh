@@ -431,6 +431,61 @@ DE_DEV float rmo_segment_majorant(float3 ext, float3 o, float3 d, float ts, floa
     return 1.001f * (ext.x * get_rayl_density(hmin) + ext.y * get_mie_density(hmin)) + ext.z * oz;
 }
 #endif
+#if !DE_EXACT
+// Altitude bands for the rmo majorant (product flavour).  Along a straight ray the altitude is convex in t, and every density fit
+// falls with altitude (ozone: rises to its 25 km peak, then falls), so inside the band [H_k, H_k+1) the densities at the band's
+// bottom (ozone: its maximum over the band) bound sigma.rho.  A tracking pass walks the bands: the free flight is sampled against
+// the current band's majorant; a flight that would leave the band is cut at the band's exit sphere and restarted there against the
+// next band's majorant (the exponential is memoryless, so the collision law is unchanged).  From space to the ground the reference's
+// sea-level majorant spends ~110 km-equivalents of candidates, the bands {0, 4, 12, 30 km} about 15.
+DE_DEV float rmo_band_majorant(const DevScene &s, float3 ext, int k) { return ext.x * s.band_dr[k] + ext.y * s.band_dm[k] + ext.z * s.band_do[k]; }
+DE_DEV int rmo_band_of(const DevScene &s, float r) {
+    int k = 0;
+#pragma unroll
+    for (int j = 1; j < kDeRmoBands; ++j) k += r >= s.band_r[j] ? 1 : 0;
+    return k;
+}
+// Distance from q (a point of the ray inside band k, |q| ~ 6.4e6 m so the quadratic resolves < 1 m) along d to where the ray leaves the
+// band, and the band it enters.  Descending rays leave through the bottom if they reach it, everything else through the top; the top
+// band has no exit (the pass ends at t_max first).
+DE_DEV float rmo_band_exit(const DevScene &s, float3 q, float3 d, int k, int &k_next) {
+    const float b = dot(q, d), r2 = dot(q, q);
+    k_next = k;
+    if (b < 0.0f && k > 0) {
+        const float rl = s.band_r[k];
+        const float disc = b * b - (r2 - rl * rl);
+        if (disc > 0.0f) { k_next = k - 1; return fmaxf(-b - sqrtf(disc), 0.0f); }
+    }
+    if (k == kDeRmoBands - 1) return 3.0e38f;
+    const float rh = s.band_r[k + 1];
+    k_next = k + 1;
+    return fmaxf(-b + sqrtf(fmaxf(b * b - (r2 - rh * rh), 0.0f)), 0.0f);
+}
+// State of a pass walking the bands: the ray parameter t, the band it is in, where it leaves it, and the majorant in force
+// (never above the whole segment's majorant m_seg).
+struct RmoWalk { float t, tlim, max_ext; int band; };
+// Advance by the optical depth tau (sampled against the majorants in force): returns the ray parameter reached, cutting the flight at
+// every band exit before t_max and continuing with what is left of tau.  `advance(t, band)` -> (t of the band's exit, next band) is a
+// functor so the kernel can keep that rarely taken code out of line.
+template <class Adv> DE_DEV float rmo_band_walk(const DevScene &s, float3 ext, float m_seg, float t_max, float tau, RmoWalk &w, Adv advance) {
+    float tn = w.t + tau / w.max_ext;
+#pragma unroll 1
+    for (int it = 0; it < 2 * kDeRmoBands + 2 && tn >= w.tlim && w.tlim < t_max; ++it) {
+        tau -= (w.tlim - w.t) * w.max_ext;
+        w.t = w.tlim;
+        const float2 adv = advance(w.t, w.band);
+        w.band = __float_as_int(adv.y); w.tlim = adv.x;
+        w.max_ext = fminf(m_seg, rmo_band_majorant(s, ext, w.band));
+        tn = w.t + fmaxf(tau, 0.0f) / w.max_ext;
+    }
+    if (tn >= w.tlim && w.tlim < t_max) {  // (never in exact arithmetic: more crossings than bands) the segment's majorant is always valid
+        w.tlim = 3.0e38f; w.max_ext = m_seg;
+        tn = w.t + fmaxf(tau, 0.0f) / w.max_ext;
+    }
+    w.t = tn;
+    return tn;
+}
+#endif
 // ---------------------------------------------------------------- spectra (volume_rendering_models.py:48-51,194-224; colour.py:51-60)
 DE_DEV float air(float wl) {
     float rcp = 1.0f / (wl * wl);
@@ -524,7 +579,9 @@ template <class R> DE_DEV float3 sample_klein_nishina_phase(float3 view, float e
     make_orthonormal_basis(view, t, b);
     return spherical_direction(st, ct, phi, t, b, view);
 }
-// volume_rendering_models.py:125-150 -- NVIDIA "approximate Mie" Draine inverse-CDF (MIT); term order kept
+// volume_rendering_models.py:125-150 -- Draine inverse CDF of "An Approximate Mie Scattering Function for Fog and Cloud Rendering";
+// term order kept.  SPDX-FileCopyrightText: Copyright (c) <2023> NVIDIA CORPORATION & AFFILIATES. All rights reserved.
+// SPDX-License-Identifier: MIT -- full notice in NOTICE.md (also covers draine_phase and cloud_params above).
 template <class R> DE_DEV float3 sample_draine(float3 view, float g, float a, R &rng) {
     float xi = rng.next();
     float g2 = g * g, g3 = g * g2, g4 = g2 * g2, g6 = g2 * g4;
@@ -754,6 +811,9 @@ DE_DEV float3 xyz_to_rgb(float3 xyz) {  // colour.py:6-10
 }
 
 // ---------------------------------------------------------------- tone mapping (OpenDRT.py, AgX.py, renderer.py:333-365)
+// openDR_transform and its helpers follow OpenDRT v0.2.2 by Jed Smith (https://github.com/jedypod/open-display-transform) as ported
+// in the reference's lib/OpenDRT.py -- License: GPL v3; the AgX functions follow Troy Sobotka's AgX (shader translation by Olivier
+// Groulx).  See NOTICE.md.
 DE_DEV float sdivf(float a, float b) { return fabsf(b) < 1e-4f ? 0.0f : a / b; }
 DE_DEV float spowf(float a, float b) { return a <= 0.0f ? a : pow_ti(a, b); }
 DE_DEV float logf10_ti(float x) { return log2_ti(x) / log2_ti(10.0f); }

@@ -13,7 +13,8 @@ namespace DE_NS {
 // CTA as in renderer.py:43-46,304; n_spp samples per launch instead of one.
 template <bool COUNT, bool PREVIEW>
 __global__ void __launch_bounds__(128) k_render_mega(DevScene s, float *__restrict__ accum, float *__restrict__ accum2, int n_spp, uint32_t seed, uint32_t first_sample,
-                                                    int x0, int y0, int w, int h) {
+                                                    int x0, int y0, int w, int h, int tile_stride, int tile_offset) {
+    if ((int)(blockIdx.x % (unsigned)tile_stride) != tile_offset) return;  // multi-GPU tile partition: another rank's film tile
     int tiles_x = (w + kDeTileW - 1) / kDeTileW;
     int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
     int px = x0 + tx * kDeTileW + (threadIdx.x & (kDeTileW - 1)), py = y0 + ty * kDeTileH + (threadIdx.x / kDeTileW);
@@ -33,17 +34,19 @@ __global__ void __launch_bounds__(128) k_render_mega(DevScene s, float *__restri
     if (accum2) { accum2[k] += acc2.x; accum2[k + 1] += acc2.y; accum2[k + 2] += acc2.z; }  // second moments (image z-test), optional
     if (COUNT) cn.flush(s.counters);
 }
-void launch_render_mega(const DevScene &s, float *accum, float *accum2, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, bool count, cudaStream_t st) {
+void launch_render_mega(const DevScene &s, float *accum, float *accum2, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, int tile_stride,
+                        int tile_offset, bool count, cudaStream_t st) {
     int tiles = ((w + kDeTileW - 1) / kDeTileW) * ((h + kDeTileH - 1) / kDeTileH);
-    if (count) k_render_mega<true, false><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h);
-    else k_render_mega<false, false><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h);
+    if (count) k_render_mega<true, false><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h, tile_stride, tile_offset);
+    else k_render_mega<false, false><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h, tile_stride, tile_offset);
 }
 // the deterministic ray-marching preview (pathtracer.py:543-685) on the same film layout: every lane runs the same
 // 64 x 16 fixed-step loops, so one thread per pixel is already converged
-void launch_render_preview(const DevScene &s, float *accum, float *accum2, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, bool count, cudaStream_t st) {
+void launch_render_preview(const DevScene &s, float *accum, float *accum2, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h, int tile_stride,
+                           int tile_offset, bool count, cudaStream_t st) {
     int tiles = ((w + kDeTileW - 1) / kDeTileW) * ((h + kDeTileH - 1) / kDeTileH);
-    if (count) k_render_mega<true, true><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h);
-    else k_render_mega<false, true><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h);
+    if (count) k_render_mega<true, true><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h, tile_stride, tile_offset);
+    else k_render_mega<false, true><<<tiles, 128, 0, st>>>(s, accum, accum2, n_spp, seed, first_sample, x0, y0, w, h, tile_stride, tile_offset);
 }
 
 #if DE_EXACT  // _render_to_image exists in IEEE source-order arithmetic only: every mode resolves through it
@@ -65,7 +68,9 @@ void launch_resolve(const DevScene &s, const float *accum, float *out, int spp, 
 // Multi-GPU resolve fused with the accumulation exchange: the partial sums of the other ranks are read
 // straight from their memory (NVLink P2P / same-device pointers) while this pixel is resolved -- no reduce pass, no
 // staging buffer.  Summation order is fixed (own, then peers in rank order), so the image is deterministic.
-struct PeerAccums { const float *p[kDeMaxPeers]; int n; };
+// With a tile partition (stride > 1) a film tile was rendered only by the ranks whose tile offset matches it, so only THEIR buffers are
+// read for its pixels: 1/stride of the peer traffic of a plain sum.
+struct PeerAccums { const float *p[kDeMaxPeers]; int off[kDeMaxPeers]; int n, stride, own_off; };
 __global__ void __launch_bounds__(256) k_resolve_peers(DevScene s, const float *__restrict__ accum, PeerAccums peers, float *__restrict__ out, int spp) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= s.W * s.H) return;
@@ -73,21 +78,24 @@ __global__ void __launch_bounds__(256) k_resolve_peers(DevScene s, const float *
     OpenDrtPar op = opendrt_params();
     AgxPar ap;
     if (s.tonemapper == 1) ap = agx_params();
-    float3 sum = LD3(accum, (size_t)idx);
+    const int tile = (j / kDeTileH) * ((s.W + kDeTileW - 1) / kDeTileW) + i / kDeTileW;
+    const int grp = tile % peers.stride;
+    float3 sum = peers.own_off == grp ? LD3(accum, (size_t)idx) : f3(0.0f, 0.0f, 0.0f);
     for (int k = 0; k < peers.n; ++k) {
+        if (peers.off[k] != grp) continue;
         const float *q = peers.p[k] + (size_t)idx * 3;
         sum.x += __ldcv(q); sum.y += __ldcv(q + 1); sum.z += __ldcv(q + 2);  // volatile-class loads: peer memory is not cached across launches
     }
     ST3(out, (size_t)idx, resolve_pixel(s, op, ap, i, j, sum, spp));
 }
-void launch_resolve_peers(const DevScene &s, const float *accum, const float *const *peers, int n_peers, float *out, int spp, cudaStream_t st) {
+void launch_resolve_peers(const DevScene &s, const float *accum, const float *const *peers, const int *peer_offsets, int n_peers, int tile_stride, int own_offset,
+                          float *out, int spp, cudaStream_t st) {
     PeerAccums pa;
-    pa.n = n_peers;
-    for (int k = 0; k < kDeMaxPeers; ++k) pa.p[k] = k < n_peers ? peers[k] : nullptr;
+    pa.n = n_peers; pa.stride = tile_stride > 0 ? tile_stride : 1; pa.own_off = tile_stride > 1 ? own_offset : 0;
+    for (int k = 0; k < kDeMaxPeers; ++k) { pa.p[k] = k < n_peers ? peers[k] : nullptr; pa.off[k] = (k < n_peers && tile_stride > 1 && peer_offsets) ? peer_offsets[k] : 0; }
     int n = s.W * s.H;
     k_resolve_peers<<<(n + 255) / 256, 256, 0, st>>>(s, accum, pa, out, spp);
 }
-
 #endif  // DE_EXACT (resolve)
 
 #if !DE_EXACT
@@ -129,6 +137,38 @@ __global__ void k_fast_rmo_majorant(int n, const float *pos, const float *dir, c
 void t_fast_rmo_majorant(const float *pos, const float *dir, const float *ts, const float *tm, const float *ext, float *out, int n, cudaStream_t st) {
     k_fast_rmo_majorant<<<(n + 127) / 128, 128, 0, st>>>(n, pos, dir, ts, tm, ext, out);
 }
+// the rmo pass's band walk (rmo_band_walk, the function the wavefront loop calls): for the ascending ray parameters tq[i][0..nq) the
+// majorant in force when the walk reaches them; out[i][j] = majorant at tq[i][j]
+__global__ void k_fast_rmo_bands(int n, DevScene s, const float *pos, const float *dir, const float *ts, const float *tm, const float *ext, const float *tq, int nq,
+                                 float *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 o = LD3(pos, i), d = LD3(dir, i), e = LD3(ext, i);
+    const float m_seg = rmo_segment_majorant(e, o, d, ts[i], tm[i]);
+    RmoWalk w;
+    w.t = ts[i];
+    const float3 q = o + d * ts[i];
+    w.band = rmo_band_of(s, sqrtf(dot(q, q)));
+    int kn;
+    w.tlim = ts[i] + rmo_band_exit(s, q, d, w.band, kn);
+    w.max_ext = fminf(m_seg, rmo_band_majorant(s, e, w.band));
+    for (int j = 0; j < nq; ++j) {
+        const float target = tq[(size_t)i * nq + j];
+        // the crossing step of rmo_band_walk, driven by position instead of optical depth
+        for (int guard = 0; guard < 4 * kDeRmoBands && target >= w.tlim && w.tlim < tm[i]; ++guard) {
+            w.t = w.tlim;
+            int k2;
+            w.tlim = w.t + rmo_band_exit(s, o + d * w.t, d, w.band, k2);
+            w.band = k2;
+            w.max_ext = fminf(m_seg, rmo_band_majorant(s, e, w.band));
+        }
+        out[(size_t)i * nq + j] = (target >= w.tlim && w.tlim < tm[i]) ? m_seg : w.max_ext;   // guard exhausted: the walk falls back to m_seg
+    }
+}
+void t_fast_rmo_bands(const DevScene &s, const float *pos, const float *dir, const float *ts, const float *tm, const float *ext, const float *tq, int nq, float *out, int n,
+                      cudaStream_t st) {
+    k_fast_rmo_bands<<<(n + 127) / 128, 128, 0, st>>>(n, s, pos, dir, ts, tm, ext, tq, nq, out);
+}
 // intersect_land of the product flavour: out3 = (1 if the prologue's miss test fired, intersection distance or -1, SDF evaluations)
 __global__ void k_fast_land(int n, DevScene s, const float *pos, const float *dir, float *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,6 +183,33 @@ __global__ void k_fast_land(int n, DevScene s, const float *pos, const float *di
     out[3 * i + 2] = (float)cn.v[C_SDF];
 }
 void t_fast_land(const DevScene &s, const float *pos, const float *dir, float *out, int n, cudaStream_t st) { k_fast_land<<<(n + 127) / 128, 128, 0, st>>>(n, s, pos, dir, out); }
+
+// ---- measured peak of the fetch path the integrator uses: tex2Dgather on a block-linear r8 map, unorm8 -> float in the TEX unit, footprints
+// inside a 64 x 64 texel window per CTA (L1-resident), independent requests.  The denominator of the bench line's texel-rate fraction.
+__global__ void __launch_bounds__(256) k_tex_gather_peak(cudaTextureObject_t obj, int w, int h, int iters, float *out) {
+    const float bx = (float)((blockIdx.x * 97u) % (unsigned)max(w - 64, 1)), by = (float)((blockIdx.x * 53u) % (unsigned)max(h - 64, 1));
+    unsigned sx = threadIdx.x * 2654435761u;
+    float acc = 0.0f;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        sx = sx * 1664525u + 1013904223u;
+        const float4 g = tex2Dgather<float4>(obj, bx + (float)((sx >> 8) & 63u), by + (float)((sx >> 16) & 63u), 0);
+        acc += (g.x + g.y) + (g.z + g.w);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+float bench_tex_gather(cudaTextureObject_t obj, int w, int h, int ctas, int iters, float *scratch, cudaStream_t st) {
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1.0f;
+    k_tex_gather_peak<<<ctas, 256, 0, st>>>(obj, w, h, iters / 8 + 1, scratch);  // warm-up
+    cudaEventRecord(e0, st);
+    k_tex_gather_peak<<<ctas, 256, 0, st>>>(obj, w, h, iters, scratch);
+    cudaEventRecord(e1, st);
+    float ms = -1.0f;
+    if (cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms;
+}
 #endif
 
 #if DE_EXACT

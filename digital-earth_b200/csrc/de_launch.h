@@ -7,9 +7,9 @@ constexpr int kDeMaxPeers = 15;  // other ranks whose accumulation buffers one r
 
 #define DE_DECLARE_COMMON                                                                                                                \
     void launch_render_mega(const DevScene &s, float *accum, float *accum2, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, \
-                            int w, int h, bool count, cudaStream_t st);                                                                  \
+                            int w, int h, int tile_stride, int tile_offset, bool count, cudaStream_t st);                                \
     void launch_render_preview(const DevScene &s, float *accum, float *accum2, int n_spp, uint32_t seed, uint32_t first_sample, int x0,     \
-                               int y0, int w, int h, bool count, cudaStream_t st);
+                               int y0, int w, int h, int tile_stride, int tile_offset, bool count, cudaStream_t st);
 
 namespace de_fast {
 DE_DECLARE_COMMON
@@ -18,11 +18,16 @@ void launch_build_cloud_max(const uint8_t *tex, int w, int h, int b, uint8_t *ou
 void t_fast_cloud_bound(const DevScene &s, const float *pos, const float *dir, const float *ts, const float *tm, float *out4, int n, cudaStream_t st);
 void t_fast_rmo_majorant(const float *pos, const float *dir, const float *ts, const float *tm, const float *ext, float *out, int n, cudaStream_t st);
 void t_fast_land(const DevScene &s, const float *pos, const float *dir, float *out3, int n, cudaStream_t st);
+void t_fast_rmo_bands(const DevScene &s, const float *pos, const float *dir, const float *ts, const float *tm, const float *ext, const float *tq, int nq, float *out, int n,
+                      cudaStream_t st);
+// ms of `ctas` x 256 threads x `iters` independent L1-resident tex2Dgather requests (-1 on error); scratch: ctas * 256 floats
+float bench_tex_gather(cudaTextureObject_t obj, int w, int h, int ctas, int iters, float *scratch, cudaStream_t st);
 }
 namespace de_exact {
 DE_DECLARE_COMMON
 void launch_resolve(const DevScene &s, const float *accum, float *out, int spp, cudaStream_t st);
-void launch_resolve_peers(const DevScene &s, const float *accum, const float *const *peers, int n_peers, float *out, int spp, cudaStream_t st);
+void launch_resolve_peers(const DevScene &s, const float *accum, const float *const *peers, const int *peer_offsets, int n_peers, int tile_stride, int own_offset,
+                          float *out, int spp, cudaStream_t st);
 void launch_prepare(const DevScene &s, DevDerived *out, cudaStream_t st);
 void launch_build_lambda(const DevScene &s, LambdaRow *lam, float *cdf, cudaStream_t st);
 // test hooks (parity arithmetic); all pointers are device pointers

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+constexpr int kDeRmoBands = 4;
+
 struct DevTex {
     const uint8_t *data;  // row-major [y][x][c], y=0 south
     int w, h, c;
@@ -51,6 +53,10 @@ struct DevScene {
     // texels, dilated by one texel for the bilinear footprint; nullptr disables it
     const uint8_t *cloud_max;
     int cm_w, cm_h, cm_b;
+    // altitude bands of the rmo tracking majorant (product flavour): band k = altitudes [band_r[k], band_r[k+1]) (radii; band 0 reaches down
+    // to the centre, the last band up to the atmosphere top) with density bounds (Rayleigh, aerosol, ozone) valid over the whole band
+    float band_r[kDeRmoBands];
+    float band_dr[kDeRmoBands], band_dm[kDeRmoBands], band_do[kDeRmoBands];
 };
 
 

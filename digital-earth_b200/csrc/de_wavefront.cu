@@ -27,8 +27,15 @@
 
 namespace de_fast {
 
+#ifndef WF_RMO_BANDS
+#define WF_RMO_BANDS 1  // altitude-band majorants for the rmo passes (de_device.cuh: rmo_band_*); costs one state word per path
+#endif
 #ifndef WF_SLOTS
-#define WF_SLOTS 1728  // path states per CTA (one CTA per SM): 189 KB of state (28 words each) + 36 KB of queues
+#if WF_RMO_BANDS
+#define WF_SLOTS 1664  // path states per CTA (one CTA per SM): 188 KB of state (29 words each) + 36 KB of queues
+#else
+#define WF_SLOTS 1728  // 28 words each
+#endif
 #endif
 #ifndef WF_WARPS
 #define WF_WARPS 32
@@ -87,7 +94,10 @@ struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
     float mdx[WF_SLOTS], mdy[WF_SLOTS], mdz[WF_SLOTS];                        // main ray direction while the NEE ray is tracked
     float nx[WF_SLOTS], ny[WF_SLOTS], nz[WF_SLOTS], m0[WF_SLOTS], m1[WF_SLOTS], m2[WF_SLOTS];  // surface normal, albedo, ocean, bathymetry
     float na[WF_SLOTS], nb[WF_SLOTS];                                         // NEE factors: phase | brdf, n.l (nb doubles as the decision-slot word)
-    float cmj[WF_SLOTS];                                                      // tracking pass: local majorant (cloud: density bound; rmo: sigma.rho bound)
+    float cmj[WF_SLOTS];                                                      // tracking pass: local majorant (cloud: density bound; rmo: sigma.rho bound of the whole segment)
+#if WF_RMO_BANDS
+    float tlim[WF_SLOTS];                                                     // rmo pass: where the ray leaves its current altitude band (draw[24:32) holds the band)
+#endif
     // per-stage MPMC ring queues of ready slots: entry = slot | (lap & 31) << 11
     uint16_t ring[ST_COUNT][WF_RING];
     unsigned int q_tail[ST_COUNT], q_head[ST_COUNT];
@@ -97,6 +107,9 @@ struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
     int work_left;
     unsigned int n_chunks;  // work units of this launch: tiles x samples x 4 quarter-tiles
     unsigned int claimed;   // chunks this CTA claimed (timeline only)
+    // drain diagnostics (timeline only): stage visits / slots handled after this CTA found the work counter exhausted
+    unsigned int dr_visits[ST_COUNT], dr_slots[ST_COUNT];
+    unsigned long long t_exhaust, t_few;  // ... when it did, and when fewer than 64 of its paths were still alive
 };
 
 struct WfParams {
@@ -108,7 +121,8 @@ struct WfParams {
     int n_spp, x0, y0, w, h, tiles_x;
     uint32_t seed, first_sample;
     unsigned long long *prof;  // counting build: per stage {cycles, visits, lanes}, + idle cycles at index ST_COUNT
-    unsigned long long *timeline;  // optional: globaltimer ns {first CTA start, first / last CTA to see the work counter exhausted,
+    unsigned long long *cta_stats;  // optional with timeline: [gridDim.x][24] per-CTA drain diagnostics
+    unsigned long long *timeline;  // optional, counting build only: globaltimer ns {first CTA start, first / last CTA to see the work counter exhausted,
                                    // first / last CTA end, min / max chunks claimed by a CTA}
 };
 
@@ -119,6 +133,12 @@ struct WfParams {
 #define WF_CHAIN 0   // >0: one-shot stages hand their largest group of successors (>= this many lanes) straight to the next stage, no queue
                      // round trip.  Measured 8-10 % SLOWER at 8/16/24 (profiles/r1_bench.md): it breaks the SM-wide phase, and the
                      // instruction cache matters more than the queue traffic.  Kept for the record, off.
+#endif
+#ifndef WF_DRAIN_FAST
+#define WF_DRAIN_FAST 0  // 1: once the work counter is exhausted bursts run until every lane is done and one-shot stages hand their
+                         // successors straight to the next stage.  Measured (profiles/r2_tail.md): the drain is NOT shorter (it is the serial
+                         // latency of the longest path, not queue hops) and the extra code costs 8 % in steady state (no_instruction stalls
+                         // 1.6 -> 2.8 per issue).  Kept for the record, off.
 #endif
 #ifndef WF_CHAIN_TOPUP
 #define WF_CHAIN_TOPUP 4  // idle lanes of a chained group that trigger a top-up from the next stage's queue
@@ -218,6 +238,13 @@ __device__ __noinline__ float2 sphere_uv_ool(float px, float py, float pz) { ret
 DE_DEV float r8_ool(const DevTex &t, float3 p) { return fetch_r8_ool(t.obj, t.w, t.h, p.x, p.y, p.z); }
 DE_DEV float3 rgb8_ool(const DevTex &t, float3 p) { return fetch_rgb8_ool(t.obj, t.w, t.h, p.x, p.y, p.z); }
 
+// band exit at ray parameter t: returns (t of the exit, next band as float bits); out of line: called rarely and under divergence
+__device__ __noinline__ float2 rmo_band_advance(const DevScene &s, float ox, float oy, float oz, float dx, float dy, float dz, float t, int k) {
+    int kn;
+    const float3 d = f3(dx, dy, dz);
+    const float ds = rmo_band_exit(s, f3(ox, oy, oz) + d * t, d, k, kn);
+    return make_float2(t + ds, __int_as_float(kn));
+}
 struct Ctx {  // per-warp context
     const DevScene &s;
     const DevDerived &dv;
@@ -336,6 +363,15 @@ DE_DEV uint32_t setup_rmo(const Ctx &c, int slot, uint32_t pk, float3 o, float3 
         const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
         c.pool.t[slot] = t_start; c.pool.tmax[slot] = t_max;
         c.pool.cmj[slot] = fminf(lr.max_ext_rmo, rmo_segment_majorant(f3(lr.ext_r, lr.ext_m, lr.ext_o), o, d, t_start, t_max));  // local majorant
+#if WF_RMO_BANDS
+        {   // altitude band of the entry point and where the ray leaves it
+            const float3 q = o + d * t_start;
+            const int k = rmo_band_of(c.s, sqrtf(dot(q, q)));
+            const float2 adv = rmo_band_advance(c.s, o.x, o.y, o.z, d.x, d.y, d.z, t_start, k);
+            c.pool.tlim[slot] = adv.x;
+            c.pool.draw[slot] = (c.pool.draw[slot] & 0xFFFFFFu) | ((uint32_t)k << 24);
+        }
+#endif
         return PK_SET_STAGE(pk, ST_RMO);
     }
     if (!ratio) {  // no atmosphere on the way: NULL event at t_start
@@ -428,7 +464,7 @@ template <bool COUNT> DE_DEV uint32_t stage_new(Ctx &c, int slot) {
     if (c.lane == 0) chunk = atomicAdd(P.next, 1u);
     chunk = __shfl_sync(full, chunk, 0);
     if (chunk >= c.pool.n_chunks) return ~0u;
-    if (P.timeline && c.lane == 0) atomicAdd(&c.pool.claimed, 1u);
+    if (COUNT && P.timeline && c.lane == 0) atomicAdd(&c.pool.claimed, 1u);
     // chunk = (tile slot * n_spp + sample) * 4 + quarter; kept in chunk units: the path index itself exceeds 32 bits for
     // 4K x 4096 spp (3.4e10 paths).  The tile comes from the list of tiles that can see the planet (k_classify_tiles).
     unsigned in_tile = (chunk & 3u) * 32u + (unsigned)c.lane, ts = chunk >> 2;
@@ -526,7 +562,10 @@ template <bool COUNT> DE_DEV void burst_sdf(Ctx &c, int slot) {
     uint32_t iter = 0u;
     auto load = [&]() { o = ld_o(c, slot); d = ld_d(c, slot); t = c.pool.t[slot]; iter = c.pool.draw[slot] >> 24; };
     if (active) load();
-    const int min_active = min(WF_MIN_ACTIVE, (__popc(__ballot_sync(full, active)) * WF_MIN_FRAC8 + 7) / 8);  // leave the burst when this few lanes are busy
+    int min_active = min(WF_MIN_ACTIVE, (__popc(__ballot_sync(full, active)) * WF_MIN_FRAC8 + 7) / 8);  // leave the burst when this few lanes are busy
+#if WF_DRAIN_FAST
+    if (!*(volatile int *)&c.pool.work_left) min_active = 1;  // draining: nothing to re-pack with
+#endif
     const float scale = c.s.land_height_scale;
     bool pending = false;
     int pend_slot = -1;
@@ -576,20 +615,32 @@ template <bool COUNT> DE_DEV void burst_track(Ctx &c, int slot, const bool IS_CL
     bool active = slot >= 0;
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1), ext = f3(0, 0, 0);
     float t = 0.0f, tmax = 0.0f, T = 1.0f, max_ext = 1.0f, inv_max = 1.0f, ext_cloud = 0.0f;
+    float tlim = 3.0e38f;   // rmo: exit of the current altitude band (cloud passes have none)
+    int band = 0;
     uint32_t pk = 0u, blk = 0u, key1 = 0u, smp = 0u;
     auto load = [&]() {
         d = ld_d(c, slot);
         t = c.pool.t[slot]; tmax = c.pool.tmax[slot]; T = c.pool.aux[slot];
         pk = c.pool.pk[slot];
         key1 = c.pool.pix[slot]; smp = c.pool.sample[slot];
-        blk = ((c.pool.draw[slot] & 0xFFFFFFu) + 3u) >> 2;  // passes start on a block boundary; trips end on one
+        const uint32_t dw = c.pool.draw[slot];
+        blk = ((dw & 0xFFFFFFu) + 3u) >> 2;  // passes start on a block boundary; trips end on one
         o = ld_o(c, slot);
-        if (IS_CLOUD) { ext_cloud = cloud_ext_of(PK_SC(pk)); max_ext = ext_cloud * c.pool.cmj[slot]; }
-        else { const LambdaRow &lr = c.s.lam[PK_LAM(pk)]; ext = f3(lr.ext_r, lr.ext_m, lr.ext_o); max_ext = c.pool.cmj[slot]; }
+        if (IS_CLOUD) { ext_cloud = cloud_ext_of(PK_SC(pk)); max_ext = ext_cloud * c.pool.cmj[slot]; tlim = 3.0e38f; }
+        else {
+            const LambdaRow &lr = c.s.lam[PK_LAM(pk)]; ext = f3(lr.ext_r, lr.ext_m, lr.ext_o); max_ext = c.pool.cmj[slot];
+#if WF_RMO_BANDS
+            band = (int)(dw >> 24); tlim = c.pool.tlim[slot];
+            max_ext = fminf(max_ext, rmo_band_majorant(c.s, ext, band));
+#endif
+        }
         inv_max = 1.0f / max_ext;
     };
     if (active) load();
-    const int min_active = min(WF_MIN_ACTIVE, (__popc(__ballot_sync(full, active)) * WF_MIN_FRAC8 + 7) / 8);  // leave the burst when this few lanes are busy
+    int min_active = min(WF_MIN_ACTIVE, (__popc(__ballot_sync(full, active)) * WF_MIN_FRAC8 + 7) / 8);  // leave the burst when this few lanes are busy
+#if WF_DRAIN_FAST
+    if (!*(volatile int *)&c.pool.work_left) min_active = 1;
+#endif
     bool pending = false;
     int pend_slot = -1;
     uint32_t pend_st = ST_RMO_DONE;
@@ -605,7 +656,17 @@ template <bool COUNT> DE_DEV void burst_track(Ctx &c, int slot, const bool IS_CL
             uint32_t ev = 0u, id = IS_CLOUD ? 3u : 0u, draw_after = 0u;
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
+#if WF_RMO_BANDS
+                if (!IS_CLOUD) {  // free flight through the altitude bands (de_device.cuh: rmo_band_walk)
+                    RmoWalk w{t, tlim, max_ext, band};
+                    t = rmo_band_walk(c.s, ext, c.pool.cmj[slot], tmax, -__logf(u32_to_unit(h ? rb.z : rb.x)), w,
+                                      [&](float tt, int kk) { return rmo_band_advance(c.s, o.x, o.y, o.z, d.x, d.y, d.z, tt, kk); });
+                    tlim = w.tlim; band = w.band;
+                    if (w.max_ext != max_ext) { max_ext = w.max_ext; inv_max = 1.0f / max_ext; }
+                } else t -= __logf(u32_to_unit(h ? rb.z : rb.x)) * inv_max;
+#else
                 t -= __logf(u32_to_unit(h ? rb.z : rb.x)) * inv_max;
+#endif
                 const float3 pos = o + d * t;  // from the origin every time: independent of where bursts were cut
                 if (t >= tmax) { done = true; draw_after = 4u * blk + 2u * h + 1u; break; }
                 float es0 = 0.0f, es1 = 0.0f, es2 = 0.0f, sum;
@@ -677,7 +738,10 @@ template <bool COUNT> DE_DEV void burst_track(Ctx &c, int slot, const bool IS_CL
     q_push_sorted(c.pool, pending, pend_st, pend_slot, c.lane);
     unsigned am = __ballot_sync(full, active);
     if (active) {
-        c.pool.t[slot] = t; if (pk & PK_RATIO) c.pool.aux[slot] = T; store_draw(c, slot, 4u * blk, 0u);
+        c.pool.t[slot] = t; if (pk & PK_RATIO) c.pool.aux[slot] = T; store_draw(c, slot, 4u * blk, (uint32_t)band);
+#if WF_RMO_BANDS
+        if (!IS_CLOUD) c.pool.tlim[slot] = tlim;
+#endif
         q_push_group(c.pool, ST_SELF, slot, am, c.lane);
     }
 }
@@ -825,9 +889,10 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         pool.q_avail[threadIdx.x] = threadIdx.x == ST_NEW ? WF_SLOTS : 0;
     }
     if (threadIdx.x == 0) {
-        pool.retired = 0; pool.work_left = 1; pool.phase = 0; pool.claimed = 0u;
+        pool.retired = 0; pool.work_left = 1; pool.phase = 0; pool.claimed = 0u; pool.t_exhaust = 0ull; pool.t_few = 0ull;
+        for (int k = 0; k < (int)ST_COUNT; ++k) { pool.dr_visits[k] = 0u; pool.dr_slots[k] = 0u; }
         pool.n_chunks = __ldg(P.n_tiles) * (unsigned)P.n_spp * 4u;
-        if (P.timeline) atomicMin(&P.timeline[0], globaltimer_ns());
+        if (COUNT && P.timeline) atomicMin(&P.timeline[0], globaltimer_ns());
     }
     __syncthreads();
     int last_st = -1;
@@ -892,14 +957,21 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
             uint32_t npk = 0u;
             bool has = slot >= 0;
             if (st == ST_NEW) {
-                if (!work_left) { if (lane == 0) atomicAdd(&pool.retired, n); continue; }
+                if (!work_left) {
+                    if (lane == 0) {
+                        const int before = atomicAdd(&pool.retired, n);
+                        if (COUNT && P.timeline && before < WF_SLOTS - 64 && before + n >= WF_SLOTS - 64) pool.t_few = globaltimer_ns();
+                    }
+                    continue;
+                }
                 if (n < 32) { q_push_sorted(pool, has, ST_NEW, slot, lane); continue; }  // lost a race for a whole chunk
                 npk = stage_new<COUNT>(c, slot);
                 if (npk == ~0u) {  // work counter exhausted
                     if (lane == 0) {
-                        if (P.timeline && atomicExch(&pool.work_left, 0) != 0) {
+                        if (COUNT && P.timeline && atomicExch(&pool.work_left, 0) != 0) {
                             const unsigned long long tn = globaltimer_ns();
                             atomicMin(&P.timeline[1], tn); atomicMax(&P.timeline[2], tn);
+                            pool.t_exhaust = tn;
                         }
                         pool.work_left = 0; atomicAdd(&pool.retired, 32);
                     }
@@ -914,18 +986,23 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
             }
             if (has) c.pool.pk[slot] = npk;
             const uint32_t tgt = PK_STAGE(npk);
-#if WF_CHAIN
+#if WF_CHAIN || WF_DRAIN_FAST
             // hand the largest group of successors straight to its stage: no queue round trip for them
             const unsigned grp = __match_any_sync(full, has ? tgt : 15u);
             const unsigned best = __reduce_max_sync(full, has ? ((unsigned)__popc(grp) << 4) | tgt : 0u);
             const uint32_t cst = best & 15u;
             const int cn_ = (int)(best >> 4);
-            if (cn_ >= WF_CHAIN && (cst != ST_NEW || cn_ == 32)) {
+#if WF_CHAIN
+            const int chain_min = WF_CHAIN;
+#else
+            const int chain_min = work_left ? 64 : 1;  // only while draining
+#endif
+            if (cn_ >= chain_min && cst != ST_NEW) {
                 const bool keep = has && tgt == cst;
                 q_push_sorted(pool, has && !keep, tgt, slot, lane);
                 if (!keep) slot = -1;
                 n = cn_;
-                if (32 - cn_ >= WF_CHAIN_TOPUP && cst != ST_NEW) {  // fill the idle lanes from the successor's queue
+                if (WF_CHAIN && 32 - cn_ >= WF_CHAIN_TOPUP && cst != ST_NEW) {  // fill the idle lanes from the successor's queue
                     int av2 = 0;
                     if (lane == 0) av2 = *(volatile int *)&pool.q_avail[cst];
                     if (__shfl_sync(full, av2, 0) > 0) {
@@ -944,6 +1021,7 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
 #endif
             q_push_sorted(pool, has, tgt, slot, lane);
         }
+        if (COUNT && P.timeline && lane == 0 && !work_left) { atomicAdd(&pool.dr_visits[st_run], 1u); atomicAdd(&pool.dr_slots[st_run], (unsigned)n_run); }
         if (COUNT && lane == 0 && P.prof) {
             atomicAdd(&P.prof[3 * st_run], (unsigned long long)(clock64() - t0s));
             atomicAdd(&P.prof[3 * st_run + 1], 1ull);
@@ -951,12 +1029,17 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         }
     }
     if (COUNT) cn.flush(s.counters);
-    if (P.timeline) {
+    if (COUNT && P.timeline) {
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned long long tn = globaltimer_ns();
             atomicMin(&P.timeline[3], tn); atomicMax(&P.timeline[4], tn);
             atomicMin(&P.timeline[5], (unsigned long long)pool.claimed); atomicMax(&P.timeline[6], (unsigned long long)pool.claimed);
+            if (P.cta_stats) {
+                unsigned long long *o = P.cta_stats + (size_t)blockIdx.x * 24;
+                o[0] = pool.t_exhaust; o[1] = pool.t_few; o[2] = tn; o[3] = pool.claimed;
+                for (int k = 0; k < (int)ST_COUNT; ++k) { o[4 + k] = pool.dr_visits[k]; o[4 + ST_COUNT + k] = pool.dr_slots[k]; }
+            }
         }
     }
 }
@@ -1003,14 +1086,15 @@ DE_DEV bool tile_is_space(const DevScene &s, const DevDerived &dv, int x0, int y
     const double phi = dangle(c, axis);
     return phi > cap + alpha + 2e-5;  // NaN (degenerate camera) compares false: generic route
 }
-// one CTA; cls[t] = 1 for space tiles, wf_list = the others in tile order, counts = {n_wf, n_space}
+// one CTA; cls[t] = 1 for space tiles, 2 for tiles of another rank (tile partition: t % stride != offset), wf_list = the rest in tile
+// order, counts = {n_wf, n_space}
 __global__ void __launch_bounds__(1024) k_classify_tiles(const __grid_constant__ DevScene s, int x0, int y0, int w, int h, int tiles_x, int n_tiles, int enable,
-                                                        unsigned char *cls, unsigned int *wf_list, unsigned int *counts) {
+                                                        int stride, int offset, unsigned char *cls, unsigned int *wf_list, unsigned int *counts) {
     __shared__ unsigned int warp_sum[32];
-    __shared__ unsigned int base_wf;
+    __shared__ unsigned int base_wf, n_space;
     const DevDerived dv = *s.derived;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) base_wf = 0u;
+    if (threadIdx.x == 0) { base_wf = 0u; n_space = 0u; }
     __syncthreads();
     for (int b = 0; b < n_tiles; b += 1024) {
         const int t = b + (int)threadIdx.x;
@@ -1018,9 +1102,11 @@ __global__ void __launch_bounds__(1024) k_classify_tiles(const __grid_constant__
         if (t < n_tiles) {
             const int tx = t % tiles_x, ty = t / tiles_x;
             const int px0 = x0 + tx * kDeTileW, py0 = y0 + ty * kDeTileH;
-            const bool space = enable && tile_is_space(s, dv, px0, py0, min(px0 + kDeTileW, x0 + w), min(py0 + kDeTileH, y0 + h));
-            cls[t] = space ? 1 : 0;
-            keep = !space;
+            const bool mine = t % stride == offset;
+            const bool space = mine && enable && tile_is_space(s, dv, px0, py0, min(px0 + kDeTileW, x0 + w), min(py0 + kDeTileH, y0 + h));
+            cls[t] = !mine ? 2 : (space ? 1 : 0);
+            keep = mine && !space;
+            if (space) atomicAdd(&n_space, 1u);
         }
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
         if (lane == 0) warp_sum[wid] = __popc(bal);
@@ -1032,7 +1118,7 @@ __global__ void __launch_bounds__(1024) k_classify_tiles(const __grid_constant__
         if (threadIdx.x == 0) { unsigned int tot = 0u; for (int k = 0; k < 32; ++k) tot += warp_sum[k]; base_wf += tot; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { counts[0] = base_wf; counts[1] = (unsigned)n_tiles - base_wf; }
+    if (threadIdx.x == 0) { counts[0] = base_wf; counts[1] = n_space; }
 }
 
 // Renderer.render for tiles that cannot see the planet: one thread per pixel, n samples in registers, one add per pixel.
@@ -1043,7 +1129,7 @@ __global__ void __launch_bounds__(1024) k_classify_tiles(const __grid_constant__
 template <bool COUNT> __global__ void __launch_bounds__(kDeTileW * kDeTileH) k_space_tiles(const __grid_constant__ DevScene s, const __grid_constant__ WfParams P,
                                                                                             const unsigned char *__restrict__ cls) {
     const unsigned tile = blockIdx.x;
-    if (!cls[tile]) return;
+    if (cls[tile] != 1) return;
     __shared__ float cdf_s[kLambdaBins];
     for (int k = threadIdx.x; k < kLambdaBins; k += blockDim.x) cdf_s[k] = s.cdf[k];
     __syncthreads();
@@ -1099,13 +1185,14 @@ struct DeWavefrontState {
     int device = 0, sm_count = 0;
     unsigned int *d_next = nullptr;
     unsigned long long *d_prof = nullptr;      // [0,32): stage profile, [32,40): launch timeline
+    unsigned long long *d_cta = nullptr;       // [sm_count][24] per-CTA drain diagnostics (timeline mode)
     bool attr_set = false;
     // tile classification, cached per (parameter version, window)
     unsigned char *d_cls = nullptr;
     unsigned int *d_wf_list = nullptr, *d_counts = nullptr;
     int tiles_cap = 0;
     unsigned long long cls_version = ~0ull;
-    int cls_win[4] = {-1, -1, -1, -1}, cls_enable = -1;
+    int cls_win[4] = {-1, -1, -1, -1}, cls_enable = -1, cls_part[2] = {-1, -1};
     // k_space_tiles runs on a side stream so its CTAs fill the SMs the persistent kernel's drain leaves idle
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1119,6 +1206,7 @@ DeWavefrontState *de_wavefront_alloc(int device) {
     if (cudaMalloc(&st->d_prof, sizeof(unsigned long long) * 40) != cudaSuccess) { cudaFree(st->d_next); delete st; return nullptr; }
     if (cudaMalloc(&st->d_counts, sizeof(unsigned int) * 2) != cudaSuccess) { cudaFree(st->d_next); cudaFree(st->d_prof); delete st; return nullptr; }
     cudaMemset(st->d_prof, 0, sizeof(unsigned long long) * 40);
+    if (cudaMalloc(&st->d_cta, sizeof(unsigned long long) * 24 * (size_t)st->sm_count) != cudaSuccess) st->d_cta = nullptr;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = numerically greatest = lowest priority
     if (cudaStreamCreateWithPriority(&st->side, cudaStreamNonBlocking, lo) != cudaSuccess) st->side = nullptr;
@@ -1130,7 +1218,7 @@ void de_wavefront_free(DeWavefrontState *st) {
     if (!st) return;
     cudaFree(st->d_next);
     cudaFree(st->d_prof);
-    cudaFree(st->d_cls); cudaFree(st->d_wf_list); cudaFree(st->d_counts);
+    cudaFree(st->d_cls); cudaFree(st->d_wf_list); cudaFree(st->d_counts); cudaFree(st->d_cta);
     if (st->side) cudaStreamDestroy(st->side);
     if (st->ev_fork) cudaEventDestroy(st->ev_fork);
     if (st->ev_join) cudaEventDestroy(st->ev_join);
@@ -1152,6 +1240,7 @@ int de_wavefront_render(DeWavefrontState *st, const DevScene &s, const DeWavefro
     const bool count = job.count;
     P.prof = count ? st->d_prof : nullptr;
     P.timeline = job.timeline ? st->d_prof + 32 : nullptr;
+    P.cta_stats = job.timeline ? st->d_cta : nullptr;
     if (count) cudaMemsetAsync(st->d_prof, 0, sizeof(unsigned long long) * 32, stream);
     if (job.timeline) {
         const unsigned long long init[8] = {~0ull, ~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull};
@@ -1167,9 +1256,10 @@ int de_wavefront_render(DeWavefrontState *st, const DevScene &s, const DeWavefro
     }
     const int enable = job.space_tiles ? 1 : 0;
     if (st->cls_version != job.param_version || st->cls_win[0] != job.x0 || st->cls_win[1] != job.y0 || st->cls_win[2] != job.w || st->cls_win[3] != job.h ||
-        st->cls_enable != enable) {
-        k_classify_tiles<<<1, 1024, 0, stream>>>(s, job.x0, job.y0, job.w, job.h, P.tiles_x, (int)tiles, enable, st->d_cls, st->d_wf_list, st->d_counts);
-        st->cls_version = job.param_version; st->cls_enable = enable;
+        st->cls_enable != enable || st->cls_part[0] != job.tile_stride || st->cls_part[1] != job.tile_offset) {
+        k_classify_tiles<<<1, 1024, 0, stream>>>(s, job.x0, job.y0, job.w, job.h, P.tiles_x, (int)tiles, enable, job.tile_stride, job.tile_offset, st->d_cls,
+                                                st->d_wf_list, st->d_counts);
+        st->cls_version = job.param_version; st->cls_enable = enable; st->cls_part[0] = job.tile_stride; st->cls_part[1] = job.tile_offset;
         st->cls_win[0] = job.x0; st->cls_win[1] = job.y0; st->cls_win[2] = job.w; st->cls_win[3] = job.h;
     }
     P.tile_list = st->d_wf_list; P.n_tiles = st->d_counts;
@@ -1202,4 +1292,9 @@ int de_wavefront_profile(DeWavefrontState *st, unsigned long long *out40) {
 int de_wavefront_tile_counts(DeWavefrontState *st, unsigned int *out2) {
     if (!st) return -1;
     return cudaMemcpy(out2, st->d_counts, sizeof(unsigned int) * 2, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+int de_wavefront_cta_stats(DeWavefrontState *st, unsigned long long *out, int max_ctas) {
+    if (!st || !st->d_cta) return -1;
+    const int n = st->sm_count < max_ctas ? st->sm_count : max_ctas;
+    return cudaMemcpy(out, st->d_cta, sizeof(unsigned long long) * 24 * (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess ? n : -2;
 }

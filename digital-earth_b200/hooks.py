@@ -85,3 +85,7 @@ class Hooks:
     def fast_cloud_bound(self, pos, d, ts, tm): return self._call("de_test_fast_cloud_bound", len(ts), (len(ts), 4), self.f(pos), self.f(d), self.f(ts), self.f(tm))
     def fast_rmo_majorant(self, pos, d, ts, tm, ext): return self._call("de_test_fast_rmo_majorant", len(ts), (len(ts),), self.f(pos), self.f(d), self.f(ts), self.f(tm), self.f(ext))
     def fast_land(self, pos, d): return self._call("de_test_fast_land", len(pos), (len(pos), 3), self.f(pos), self.f(d))
+
+    def fast_rmo_bands(self, pos, d, ts, tm, ext, tq):
+        tq = np.ascontiguousarray(tq, np.float32)
+        return self._call("de_test_fast_rmo_bands", len(ts), tq.shape, self.f(pos), self.f(d), self.f(ts), self.f(tm), self.f(ext), self.f(tq), int(tq.shape[1]))

@@ -4,7 +4,8 @@
         --textures synthetic:8192x4096 --out florida.png
     torchrun --nproc-per-node 8 -m digital_earth_b200.render --config ... --orbit 120 --out-dir frames/
 
-One process per GPU.  A still frame is split by sample slice across ranks and sum-reduced with NCCL;
+One process per GPU.  A still frame is split by sample slice (or --tile-groups: film-tile groups x sample
+slices) across ranks and sum-reduced with NCCL;
 an orbit (camera and look-at rotated about +Y, BASELINE configs[4]) is sharded by frame, no collective.
 """
 import argparse
@@ -48,13 +49,15 @@ def main(argv=None):
     ap.add_argument("--tonemapper", default="opendrt", choices=["opendrt", "agx"])
     ap.add_argument("--save-accum", default=None, help=".npz checkpoint of the linear accumulation buffer + spp")
     ap.add_argument("--resume", default=None, help="continue a still from a --save-accum checkpoint: --spp is the new total")
+    ap.add_argument("--tile-groups", type=int, default=1, help="multi-GPU still: interleaved 16x8 film-tile groups x sample slices (1 = sample slices only)")
+    ap.add_argument("--no-frames", action="store_true", help="orbit: render and resolve every frame but do not write the PNGs (throughput runs)")
     a = ap.parse_args(argv)
 
     import numpy as np
     import torch
     import torch.distributed as dist
     from . import Renderer, load_config, save_screenshot
-    from .distributed import frame_shard, reduce_accumulation, sample_slice
+    from .distributed import frame_shard, partition, reduce_accumulation
 
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -66,13 +69,13 @@ def main(argv=None):
     r.tonemapper = 1 if a.tonemapper == "agx" else 0
     r.copy_textures()
 
-    def render_slice(first, n, keep=False):
+    def render_slice(first, n, keep=False, tiles=None):
         if not keep:
             r.reset_framebuffer()
         done = 0
         while done < n:
             k = min(a.batch, n - done)
-            r.accumulate(k, first_sample=first + done)
+            r.accumulate(k, first_sample=first + done, tiles=tiles)
             done += k
 
     if a.orbit:
@@ -85,20 +88,34 @@ def main(argv=None):
             render_slice(0, a.spp)
             img = r.fetch_image(spp=a.spp)
             e1.record()
-            save_screenshot(img, os.path.join(a.out_dir, "frame_%04d.png" % f))
+            if a.no_frames:
+                torch.cuda.synchronize()
+            else:
+                save_screenshot(img, os.path.join(a.out_dir, "frame_%04d.png" % f))
             dev_ms += e0.elapsed_time(e1)
         if mine:
             print("rank %d: %d frames of %dx%d x %d spp, %.1f ms/frame on the device (%.2f frames/s, %.1f M samples/s)"
                   % (rank, len(mine), W, H, a.spp, dev_ms / len(mine), 1e3 * len(mine) / dev_ms, W * H * a.spp * len(mine) / dev_ms / 1e3), flush=True)
+        # whole-job figure: frames are independent, the job ends when the slowest rank has rendered its share (device time, max over ranks)
+        tot = torch.tensor([dev_ms], device=r.device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            import json
+            print(json.dumps({"flythrough": {"frames": a.orbit, "res": a.res, "spp": a.spp, "n_gpus": world, "device_ms_max_over_ranks": float(tot.item()),
+                                             "frames_per_s": 1e3 * a.orbit / float(tot.item()), "path_samples_per_s": W * H * a.spp * a.orbit / (float(tot.item()) * 1e-3),
+                                             "sharding": "frame f -> rank f mod N, no collective"}}), flush=True)
     else:
         r.apply_config(cfg)
         have = 0
         if a.resume:  # rank 0 carries the old sums; every rank renders its share of the NEW samples [have, spp)
-            have = r.load_accumulation(a.resume) if rank == 0 else int(np.load(a.resume)["spp"])
+            # every rank validates the checkpoint against ITS renderer (resolution, seed, scene, textures, integrator); rank 0 loads it
+            have = r.load_accumulation(a.resume) if rank == 0 else r.check_checkpoint(a.resume)
             if have > a.spp:
                 raise SystemExit("checkpoint already holds %d spp, --spp %d asks for fewer" % (have, a.spp))
-        first, n = sample_slice(a.spp - have, rank, world)
-        render_slice(have + first, n, keep=bool(a.resume) and rank == 0)
+        part = partition(a.spp - have, rank, world, a.tile_groups)
+        render_slice(have + part["first_sample"], part["n_spp"], keep=bool(a.resume) and rank == 0,
+                     tiles=(part["tile_stride"], part["tile_offset"]) if a.tile_groups > 1 else None)
         reduce_accumulation(r.color_buffer, dst=0)
         if rank == 0:
             r.current_spp = a.spp

@@ -172,6 +172,29 @@ class Renderer:
                 "min_chunks_per_cta": int(buf[5]), "max_chunks_per_cta": int(buf[6]),
                 "wavefront_tiles": int(buf[7]) & 0xFFFFFFFF, "space_tiles": int(buf[7]) >> 32}
 
+    def tex_gather_peak(self, slot=3, iters=4096):
+        """Measured peak of the integrator's fetch instruction (tex2Dgather, L1-resident footprints) in requests/s."""
+        if not self._textures_copied:
+            self.copy_textures()
+        self._bind_stream()
+        v = C.c_double()
+        self._check(self._lib.de_bench_tex_gather(self._ctx, int(slot), int(iters), C.byref(v)))
+        return float(v.value)
+
+    def cta_timeline(self):
+        """Per-CTA drain diagnostics of the last wavefront accumulate() with option `timeline`: list of dicts, times in ms after the
+        launch's first CTA start."""
+        t0 = np.zeros(8, np.uint64)
+        self._check(self._lib.de_get_launch_timeline(self._ctx, t0.ctypes.data_as(C.c_void_p)))
+        buf = np.zeros((256, 24), np.uint64)
+        n = self._lib.de_get_cta_timeline(self._ctx, buf.ctypes.data_as(C.c_void_p), 256)
+        if n < 0:
+            self._check(n)
+        names = ("NEW", "SDF", "RMO", "CLOUD", "SDF_DONE", "RMO_DONE", "EVENT", "NEE_DONE", "SURFACE")
+        ms = lambda v: (int(v) - int(t0[0])) * 1e-6 if int(v) else float("nan")  # noqa: E731
+        return [{"exhaust_ms": ms(b[0]), "few_ms": ms(b[1]), "end_ms": ms(b[2]), "chunks": int(b[3]),
+                 "visits": {k: int(b[4 + i]) for i, k in enumerate(names)}, "slots": {k: int(b[13 + i]) for i, k in enumerate(names)}} for b in buf[:n]]
+
     def set_mode(self, mode):
         """'wavefront' (product), 'megakernel' (1 thread/pixel baseline) or 'parity' (IEEE source-order)."""
         self.mode = mode
@@ -274,16 +297,22 @@ class Renderer:
         self.current_spp = 0
         self._check(self._lib.de_reset(self._ctx))
 
-    def accumulate(self, n_spp=1, window=None, first_sample=None):
+    def accumulate(self, n_spp=1, window=None, first_sample=None, tiles=None):
         """renderer.py:371-380 (+1 spp); n_spp > 1 renders several samples per pixel in one launch.
-        first_sample: Philox sample index of the first sample (default: current_spp)."""
+        first_sample: Philox sample index of the first sample (default: current_spp).
+        tiles=(stride, offset): only the 16x8 film tiles t with t % stride == offset (multi-GPU tile partition)."""
         if not self._textures_copied:
             self.copy_textures()
         self._bind_stream()
         self._push_params()
-        x0, y0, w, h = window or (0, 0, self.image_res[0], self.image_res[1])
         fs = self.current_spp if first_sample is None else int(first_sample)
-        self._check(self._lib.de_accumulate(self._ctx, int(n_spp), self.seed & 0xFFFFFFFF, fs & 0xFFFFFFFF, x0, y0, w, h))
+        if tiles is not None:
+            if window is not None:
+                raise ValueError("a tile partition covers the whole frame: pass either window or tiles")
+            self._check(self._lib.de_accumulate_tiles(self._ctx, int(n_spp), self.seed & 0xFFFFFFFF, fs & 0xFFFFFFFF, int(tiles[0]), int(tiles[1])))
+        else:
+            x0, y0, w, h = window or (0, 0, self.image_res[0], self.image_res[1])
+            self._check(self._lib.de_accumulate(self._ctx, int(n_spp), self.seed & 0xFFFFFFFF, fs & 0xFFFFFFFF, x0, y0, w, h))
         self.current_spp += int(n_spp)
 
     def fetch_image(self, accum=None, spp=None):
@@ -314,16 +343,22 @@ class Renderer:
     def close_peers(self):
         self._check(self._lib.de_ipc_close_peers(self._ctx))
 
-    def fetch_image_peers(self, peers, spp):
+    def fetch_image_peers(self, peers, spp, tile_stride=1, own_offset=0, peer_offsets=None):
         """fetch_image() of (own buffer + the peers' buffers): one kernel reads the other ranks' partial sums over
-        NVLink peer memory while it resolves.  peers: device addresses (open_peer) or CUDA tensors [H][W][3] f32."""
+        NVLink peer memory while it resolves.  peers: device addresses (open_peer) or CUDA tensors [H][W][3] f32.
+        With a tile partition (tile_stride > 1) every pixel reads only the buffers of the ranks that rendered its tile."""
         if not self._textures_copied:
             self.copy_textures()
         self._bind_stream()
         self._push_params()
         addrs = [int(p.data_ptr()) if hasattr(p, "data_ptr") else int(p) for p in peers]
         arr = (C.c_void_p * max(len(addrs), 1))(*addrs)
-        self._check(self._lib.de_resolve_peers(self._ctx, arr, len(addrs), C.c_void_p(self._image.data_ptr()), max(int(spp), 1)))
+        offs = list(peer_offsets) if peer_offsets is not None else [0] * len(addrs)
+        if len(offs) != len(addrs):
+            raise ValueError("peer_offsets needs one entry per peer")
+        oarr = (C.c_int * max(len(addrs), 1))(*offs)
+        self._check(self._lib.de_resolve_peers_tiled(self._ctx, arr, oarr, len(addrs), int(tile_stride), int(own_offset),
+                                                     C.c_void_p(self._image.data_ptr()), max(int(spp), 1)))
         return self._image.permute(1, 0, 2)
 
     @property
@@ -336,26 +371,56 @@ class Renderer:
 
     # progressive checkpoint: the linear accumulation buffer + the sample count is the
     # whole state of a progressive render, because a pixel's sample k is the same path in every launch
+    def _accumulation_signature(self):
+        """Everything the accumulated radiance depends on: camera, sun, terrain scale, integrator family and the texture set.
+        (Exposure, gamma, response curve and tone mapper only act in fetch_image and may change between sessions.)"""
+        import zlib
+        p = self._params()
+        scene = [float(x) for x in (*p.cam_pos, *p.look_at, *p.up, p.fov, p.aspect_scale, p.sun_angle, p.sun_path_rot, p.land_height_scale)] + [int(p.topo_tex_w)]
+        tex = {}
+        for name in _lib.TEX_SLOTS:
+            t = self._textures[name]
+            step = max(t.shape[0] // 64, 1), max(t.shape[1] // 128, 1)            # a 64 x 128 sub-grid identifies the map cheaply
+            tex[name] = [list(t.shape), int(zlib.crc32(np.ascontiguousarray(t[::step[0], ::step[1]]).tobytes()))]
+        return {"scene": scene, "integrator": "preview" if self.mode == "preview" else "path_tracer", "textures": tex}
+
     def save_accumulation(self, path, extra=None):
-        """Write {accum [H][W][3] f32, spp, seed, image_res, params} to an .npz; returns the path."""
-        import numpy as np
+        """Write {accum [H][W][3] f32, spp, seed, image_res, signature of scene + textures + integrator} to an .npz; returns the path."""
+        import json
         self.sync()
         meta = dict(extra or {})
         np.savez_compressed(path, accum=self._accum.cpu().numpy(), spp=np.int64(self.current_spp), seed=np.int64(self.seed),
-                            image_res=np.asarray(self.image_res, np.int64), meta=np.array(sorted(map(str, meta.items()))))
+                            image_res=np.asarray(self.image_res, np.int64), meta=np.array(sorted(map(str, meta.items()))),
+                            signature=np.array(json.dumps(self._accumulation_signature(), sort_keys=True)))
         return path if str(path).endswith(".npz") else str(path) + ".npz"
 
-    def load_accumulation(self, path):
-        """Resume from save_accumulation(): the next accumulate() continues at sample index `spp`."""
-        import numpy as np
-        import torch
+    def check_checkpoint(self, path):
+        """Validate a checkpoint against this renderer WITHOUT loading it (every rank of a distributed resume calls this): resolution,
+        seed, and -- when the file carries one -- the scene / texture / integrator signature.  Returns its spp; raises ValueError."""
+        import json
         with np.load(path) as z:
-            acc, spp, seed = z["accum"], int(z["spp"]), int(z["seed"]) if "seed" in z else self.seed
-            res = tuple(int(x) for x in z["image_res"]) if "image_res" in z else (acc.shape[1], acc.shape[0])
-        if tuple(res) != tuple(self.image_res) or acc.shape != tuple(self._accum.shape):
+            spp, seed = int(z["spp"]), int(z["seed"]) if "seed" in z else self.seed
+            res = tuple(int(x) for x in z["image_res"]) if "image_res" in z else tuple(z["accum"].shape[1::-1])
+            sig = json.loads(str(z["signature"])) if "signature" in z else None
+        if tuple(res) != tuple(self.image_res):
             raise ValueError("checkpoint is %dx%d, renderer is %dx%d" % (res[0], res[1], self.image_res[0], self.image_res[1]))
         if seed != self.seed:
             raise ValueError("checkpoint was rendered with seed %d, renderer has seed %d: resuming would repeat or skip sample streams" % (seed, self.seed))
+        if sig is not None:
+            mine = json.loads(json.dumps(self._accumulation_signature(), sort_keys=True))
+            for key in ("scene", "integrator", "textures"):
+                if sig.get(key) != mine[key]:
+                    raise ValueError("checkpoint was rendered with a different %s: resuming would mix two images into one accumulation" % key)
+        return spp
+
+    def load_accumulation(self, path):
+        """Resume from save_accumulation(): the next accumulate() continues at sample index `spp`."""
+        import torch
+        spp = self.check_checkpoint(path)
+        with np.load(path) as z:
+            acc = z["accum"]
+        if acc.shape != tuple(self._accum.shape):
+            raise ValueError("checkpoint buffer has shape %s, renderer expects %s" % (acc.shape, tuple(self._accum.shape)))
         self._bind_stream()
         self._accum.copy_(torch.from_numpy(np.ascontiguousarray(acc, dtype=np.float32)))
         self.current_spp = spp

@@ -106,7 +106,8 @@ int de_set_mode(de_ctx *ctx, int mode);
  *   "space_async"     1 (default) ... on a side stream, overlapping the persistent kernel's drain
  *   "moments"         1 = keep per-pixel sums of squared sample contributions beside the accumulation buffer (image z-test,
  *                     SURVEY 8d); de_get_moment2 returns the buffer; de_reset clears it
- *   "timeline"        1 = record the wavefront kernel's launch timeline (de_get_launch_timeline)
+ *   "timeline"        1 = record the wavefront kernel's launch timeline (de_get_launch_timeline); the instrumented build records
+ *                     it, so de_set_counting(ctx, 1) must be on as well
  *   "linear_textures" 0 = release the row-major texture copies (read by the parity flavour and the hooks only) */
 int de_set_option(de_ctx *ctx, const char *name, int value);
 
@@ -125,6 +126,10 @@ int de_reset(de_ctx *ctx);
  * n_spp samples per pixel with sample indices [first_sample, first_sample+n_spp) over the pixel
  * window [x0,x0+w) x [y0,y0+h) (whole frame: 0,0,W,H).  Adds into the ctx accumulation buffer. */
 int de_accumulate(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, int x0, int y0, int w, int h);
+/* Multi-GPU tile partition (the film tile is the reference's 16x8 block, renderer.py:43-46,304-305): the whole frame,
+ * but only the film tiles t = ty * ceil(W/16) + tx with t % tile_stride == tile_offset.  Ranks with different offsets write
+ * disjoint pixels; combine with an spp slice through first_sample / n_spp (e.g. 8 GPUs = 2 tile groups x 4 sample slices). */
+int de_accumulate_tiles(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first_sample, int tile_stride, int tile_offset);
 /* device pointer of the accumulation buffer ([H][W][3] f32 linear sRGB sums; color_buffer,
  * renderer.py:25,330) so the caller can view it as a tensor / hand it to NCCL */
 int de_get_accum(de_ctx *ctx, float **dev_ptr);
@@ -151,6 +156,10 @@ int de_ipc_export_accum(de_ctx *ctx, void *handle64);
 int de_ipc_open_peer(de_ctx *ctx, const void *handle64, float **dev_ptr);
 int de_ipc_close_peers(de_ctx *ctx);
 int de_resolve_peers(de_ctx *ctx, const float *const *peer_accums, int n_peers, float *dev_out, int spp_total);
+/* de_resolve_peers for a tile (+ spp) partition: peer k rendered the tiles with t % tile_stride == peer_tile_offsets[k], this rank
+ * those with own_tile_offset; a pixel only reads the buffers of the ranks that rendered its tile (1/stride of the peer traffic). */
+int de_resolve_peers_tiled(de_ctx *ctx, const float *const *peer_accums, const int *peer_tile_offsets, int n_peers, int tile_stride, int own_tile_offset,
+                           float *dev_out, int spp_total);
 /* convenience for non-torch callers: resolve + copy to host memory, synchronous */
 int de_fetch_image_host(de_ctx *ctx, float *host_out, int spp_total);
 int de_sync(de_ctx *ctx);
@@ -164,6 +173,14 @@ int de_get_stage_profile(de_ctx *ctx, uint64_t *out32);
  * out8 = {first CTA start, first CTA to find the work counter exhausted, last CTA to, first CTA end, last CTA end,
  *         min chunks claimed by a CTA, max chunks, (space tiles << 32) | tiles rendered by the persistent kernel} */
 int de_get_launch_timeline(de_ctx *ctx, uint64_t *out8);
+
+/* measurement aid for the bench line's texel-rate roofline: sustained rate of the integrator's own fetch instruction (tex2Dgather on the
+ * block-linear copy of texture `slot`, footprints L1-resident, all SMs saturated), in gather requests per second (4 texels each) */
+int de_bench_tex_gather(de_ctx *ctx, int slot, int iters, double *gathers_per_second);
+/* per-CTA drain diagnostics of the same launch: out[24 * k + ...] = {ns when CTA k found the counter exhausted, ns when fewer than 64
+ * of its paths were alive, ns at its end, chunks claimed, stage visits[9], slots handled[9] after exhaustion}; returns the number
+ * of CTAs written (>= 0) or a DE_ERR_* code */
+int de_get_cta_timeline(de_ctx *ctx, uint64_t *out, int max_ctas);
 
 /* ---- test hooks: the deterministic sub-paths of SURVEY 8(a), DEVICE pointers, n items --------
  * Each evaluates the IEEE source-order (parity) flavour of one reference function. */
@@ -200,6 +217,10 @@ int de_test_trace_preview(de_ctx *, const int32_t *px, const int32_t *py, const 
 int de_test_fast_cloud_bound(de_ctx *, const float *pos3, const float *dir3, const float *t_start, const float *t_max, float *out4, int n);
 /* rmo_segment_majorant: bound of sigma.rho (extinctions ext3) over [t_start, t_max] */
 int de_test_fast_rmo_majorant(de_ctx *, const float *pos3, const float *dir3, const float *t_start, const float *t_max, const float *ext3, float *out, int n);
+/* the altitude-band walk of an rmo pass (rmo_band_walk, as the wavefront loop runs it): t_query[n][n_query] ascending ray parameters in
+ * [t_start, t_max]; out[n][n_query] = the majorant in force when the walk is at that parameter */
+int de_test_fast_rmo_bands(de_ctx *, const float *pos3, const float *dir3, const float *t_start, const float *t_max, const float *ext3, const float *t_query,
+                           int n_query, float *out, int n);
 /* product-flavour intersect_land: out3 = (1 if land_surely_missed fired, distance or -1, SDF evaluations) */
 int de_test_fast_land(de_ctx *, const float *pos3, const float *dir3, float *out3, int n);
 int de_test_trace_paths(de_ctx *, const int32_t *px, const int32_t *py, const uint32_t *sample, uint32_t seed, float *out5, int n);

@@ -335,6 +335,9 @@ static float hg_phase(float c, float g) {
     return (1 - g * g) / ((float)(4.0 * 3.141592653589793) * pow_ti(1.0f + g * g - 2 * g * c, 1.5f));
 }
 /* :121-122 */
+/* draine_phase, cloud_params, sample_draine: "An Approximate Mie Scattering Function for Fog and Cloud Rendering" as included in
+ * volume_rendering_models.py:99-183.  SPDX-FileCopyrightText: Copyright (c) <2023> NVIDIA CORPORATION & AFFILIATES. All rights
+ * reserved.  SPDX-License-Identifier: MIT -- full notice in NOTICE.md. */
 static float draine_phase(float c, float g, float a) {
     return ((1 - g * g) * (1 + a * c * c)) / (4.f * (1 + (a * (1 + 2 * g * g)) / 3.f) * PI_F * pow_ti(1 + g * g - 2 * g * c, 1.5f));
 }
@@ -1011,6 +1014,8 @@ static v3 render_sample2(const orc_scene *s, const scene_params *sc, int u, int 
 }
 
 /* ------------------------------------------------------- tonemap (a17) -- */
+/* The OpenDRT functions below follow OpenDRT v0.2.2 by Jed Smith (https://github.com/jedypod/open-display-transform) as ported in
+ * lib/OpenDRT.py -- License: GPL v3 (NOTICE.md). */
 /* OpenDRT.py:92-97 */
 static float sdivf(float a, float b) { return fabsf(b) < 1e-4f ? 0.0f : a / b; }
 /* OpenDRT.py:111-116 */

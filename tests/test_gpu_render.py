@@ -459,3 +459,65 @@ def test_4096spp_rel_rmse_wavefront_vs_oracle(de, tex, scene):
     assert rel_rmse_big < 0.01, (rel_rmse_big, noise_big)       # the 1 % gate
     assert rel_rmse < 1.3 * noise + 0.002, (rel_rmse, noise)
     assert abs(z.mean()) < 0.35 and np.mean(np.abs(z) > 4.0) < 0.02, (z.mean(), np.mean(np.abs(z) > 4.0))
+
+
+@pytest.mark.parametrize("mode", ["wavefront", "megakernel"])
+def test_tile_partition_is_disjoint_and_sums_to_the_frame(de, tex, mode):
+    """SURVEY.md 8e tile (+ spp) partition on one device: the interleaved tile groups write disjoint pixels, their sum over all
+    (group, sample slice) pairs is the single-launch frame, and the tiled peer resolve (each pixel reads only the buffers of the
+    ranks that rendered its tile) equals the resolve of the summed buffer bit for bit."""
+    import torch
+    from digital_earth_b200 import distributed as dd
+    spp, world, groups = 6, 4, 2
+    r = make(de, tex, "Apollo 11", mode, 256, 128)
+    r.reset_framebuffer(); r.accumulate(spp)
+    whole = r.color_buffer.clone()
+    tx, ty = dd.tile_grid(256, 128)
+    tile_of = (torch.arange(128, device=whole.device)[:, None] // 8) * tx + torch.arange(256, device=whole.device)[None, :] // 16
+    parts, offs = [], []
+    for rank in range(world):
+        p = dd.partition(spp, rank, world, groups)
+        dd.render_partition(r, p)
+        buf = r.color_buffer.clone()
+        assert float(buf[(tile_of % groups) != p["tile_offset"]].abs().sum()) == 0.0      # nothing outside the rank's tiles
+        assert float(buf[(tile_of % groups) == p["tile_offset"]].abs().sum()) > 0.0
+        parts.append(buf); offs.append(p["tile_offset"])
+    total = parts[0] + parts[1] + parts[2] + parts[3]
+    assert pixel_agreement(total.cpu().numpy(), whole.cpu().numpy(), rel=1e-4) > 0.999
+    # peer resolve: rank 0 owns parts[0]; plain sum of everything vs. the tile-aware read
+    want = r.fetch_image(accum=total, spp=spp).clone()
+    r.color_buffer.copy_(parts[0])
+    got = r.fetch_image_peers(parts[1:], spp, tile_stride=groups, own_offset=offs[0], peer_offsets=offs[1:]).clone()
+    assert torch.allclose(got, want, rtol=0, atol=2e-6)
+    got_plain = r.fetch_image_peers(parts[1:], spp).clone()
+    assert torch.allclose(got_plain, want, rtol=0, atol=2e-6)
+    with pytest.raises(Exception):
+        r.accumulate(1, tiles=(2, 2))
+    r.close()
+
+
+def test_checkpoint_refuses_another_scene_texture_set_or_integrator(de, tex, tmp_path):
+    """a checkpoint only continues the render it came from -- same camera / sun, same maps, same integrator family."""
+    r = make(de, tex, "florida", "wavefront")
+    r.reset_framebuffer(); r.accumulate(2)
+    ck = r.save_accumulation(str(tmp_path / "ck.npz"))
+    assert r.check_checkpoint(ck) == 2
+    r.set_exposure(1.0); r.set_crf(3); r.tonemapper = 1
+    assert r.check_checkpoint(ck) == 2                       # display-side parameters may change between sessions
+    r.set_sun_angle(0.3)
+    with pytest.raises(ValueError, match="scene"):
+        r.load_accumulation(ck)
+    r.close()
+    r2 = make(de, tex, "sunset hurricane", "wavefront")
+    with pytest.raises(ValueError, match="scene"):
+        r2.check_checkpoint(ck)
+    r2.close()
+    other = de.textures.synthetic(TW, TH, cloud_cover=0.6, seed=4)
+    r3 = make(de, other, "florida", "wavefront")
+    with pytest.raises(ValueError, match="textures"):
+        r3.check_checkpoint(ck)
+    r3.close()
+    r4 = make(de, tex, "florida", "preview")
+    with pytest.raises(ValueError, match="integrator"):
+        r4.check_checkpoint(ck)
+    r4.close()

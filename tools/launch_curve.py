@@ -23,6 +23,7 @@ ap.add_argument("--scenes", default="Apollo 11,florida,sunset hurricane")
 ap.add_argument("--variants", default="space_tiles=0;space_tiles=1,space_async=0;space_tiles=1,space_async=1")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--flush", action="store_true", help="evict L2 before every timed launch")
+ap.add_argument("--cta", type=int, default=0, help="print the drain diagnostics of the N slowest CTAs (and the fastest) per timeline launch")
 a = ap.parse_args()
 W, H = map(int, a.res.split("x"))
 tw, th = map(int, a.tex.split("x"))
@@ -57,6 +58,7 @@ for scene in a.scenes.split(","):
         print("  [%s]  " % variant + "  ".join("%dspp %.2fms" % (n, m) for n, m in zip(spps, ms)) + "   fit(>=8spp): %.3f ms/spp + %.2f ms  -> %.1f Mpaths/s asymptotic"
               % (b, c, W * H / b / 1e3), flush=True)
         r.set_option("timeline", 1)
+        r.set_counting(True)        # the timeline is recorded by the instrumented build of the kernel
         for n in [int(x) for x in a.timeline_spps.split(",")]:
             r.reset_framebuffer()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -65,5 +67,11 @@ for scene in a.scenes.split(","):
             print("    timeline %4d spp: event %.2f ms | counter exhausted %.2f..%.2f ms, CTAs end %.2f..%.2f ms, chunks/CTA %d..%d, tiles wf %d space %d"
                   % (n, e0.elapsed_time(e1), t["first_exhaust_ms"], t["last_exhaust_ms"], t["first_cta_end_ms"], t["last_cta_end_ms"], t["min_chunks_per_cta"],
                      t["max_chunks_per_cta"], t["wavefront_tiles"], t["space_tiles"]), flush=True)
+            if a.cta:
+                ct = sorted(r.cta_timeline(), key=lambda c: -c["end_ms"])
+                for c in ct[:a.cta] + ct[-1:]:
+                    print("      CTA end %.2f ms (exhaust %.2f, <64 alive at %.2f): visits after exhaustion " % (c["end_ms"], c["exhaust_ms"], c["few_ms"])
+                          + " ".join("%s %d/%d" % (k, c["visits"][k], c["slots"][k]) for k in c["visits"]), flush=True)
         r.set_option("timeline", 0)
+        r.set_counting(False)
     r.close()
