@@ -446,27 +446,31 @@ DE_DEV int rmo_band_of(const DevScene &s, float r) {
     return k;
 }
 // Distance from q (a point of the ray inside band k, |q| ~ 6.4e6 m so the quadratic resolves < 1 m) along d to where the ray leaves the
-// band, and the band it enters.  Descending rays leave through the bottom if they reach it, everything else through the top; the top
-// band has no exit (the pass ends at t_max first).
-DE_DEV float rmo_band_exit(const DevScene &s, float3 q, float3 d, int k, int &k_next) {
+// band.  Descending rays leave through the bottom if they reach it, everything else through the top; the top band has no exit (the pass
+// ends at t_max first).
+DE_DEV float rmo_band_exit(const DevScene &s, float3 q, float3 d, int k) {
     const float b = dot(q, d), r2 = dot(q, q);
-    k_next = k;
     if (b < 0.0f && k > 0) {
         const float rl = s.band_r[k];
         const float disc = b * b - (r2 - rl * rl);
-        if (disc > 0.0f) { k_next = k - 1; return fmaxf(-b - sqrtf(disc), 0.0f); }
+        if (disc > 0.0f) return fmaxf(-b - sqrtf(disc), 0.0f);
     }
     if (k == kDeRmoBands - 1) return 3.0e38f;
     const float rh = s.band_r[k + 1];
-    k_next = k + 1;
     return fmaxf(-b + sqrtf(fmaxf(b * b - (r2 - rh * rh), 0.0f)), 0.0f);
+}
+// At the exit point q of band k: the band the ray enters (a sphere about the centre is left inwards only while descending, outwards only
+// while ascending) and the distance to THAT band's exit.
+DE_DEV float rmo_band_cross(const DevScene &s, float3 q, float3 d, int k, int &k_new) {
+    k_new = min(max(k + (dot(q, d) < 0.0f ? -1 : 1), 0), kDeRmoBands - 1);
+    return rmo_band_exit(s, q, d, k_new);
 }
 // State of a pass walking the bands: the ray parameter t, the band it is in, where it leaves it, and the majorant in force
 // (never above the whole segment's majorant m_seg).
 struct RmoWalk { float t, tlim, max_ext; int band; };
 // Advance by the optical depth tau (sampled against the majorants in force): returns the ray parameter reached, cutting the flight at
-// every band exit before t_max and continuing with what is left of tau.  `advance(t, band)` -> (t of the band's exit, next band) is a
-// functor so the kernel can keep that rarely taken code out of line.
+// every band exit before t_max and continuing with what is left of tau.  `advance(t, band)` -> (t of the NEW band's exit, new band), called
+// at the exit point t of `band`, is a functor so the kernel can keep that rarely taken code out of line.
 template <class Adv> DE_DEV float rmo_band_walk(const DevScene &s, float3 ext, float m_seg, float t_max, float tau, RmoWalk &w, Adv advance) {
     float tn = w.t + tau / w.max_ext;
 #pragma unroll 1

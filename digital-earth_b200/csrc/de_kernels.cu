@@ -149,8 +149,7 @@ __global__ void k_fast_rmo_bands(int n, DevScene s, const float *pos, const floa
     w.t = ts[i];
     const float3 q = o + d * ts[i];
     w.band = rmo_band_of(s, sqrtf(dot(q, q)));
-    int kn;
-    w.tlim = ts[i] + rmo_band_exit(s, q, d, w.band, kn);
+    w.tlim = ts[i] + rmo_band_exit(s, q, d, w.band);
     w.max_ext = fminf(m_seg, rmo_band_majorant(s, e, w.band));
     for (int j = 0; j < nq; ++j) {
         const float target = tq[(size_t)i * nq + j];
@@ -158,7 +157,7 @@ __global__ void k_fast_rmo_bands(int n, DevScene s, const float *pos, const floa
         for (int guard = 0; guard < 4 * kDeRmoBands && target >= w.tlim && w.tlim < tm[i]; ++guard) {
             w.t = w.tlim;
             int k2;
-            w.tlim = w.t + rmo_band_exit(s, o + d * w.t, d, w.band, k2);
+            w.tlim = w.t + rmo_band_cross(s, o + d * w.t, d, w.band, k2);
             w.band = k2;
             w.max_ext = fminf(m_seg, rmo_band_majorant(s, e, w.band));
         }

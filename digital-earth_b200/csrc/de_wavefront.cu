@@ -28,7 +28,10 @@
 namespace de_fast {
 
 #ifndef WF_RMO_BANDS
-#define WF_RMO_BANDS 1  // altitude-band majorants for the rmo passes (de_device.cuh: rmo_band_*); costs one state word per path
+#define WF_RMO_BANDS 0  // 1: altitude-band majorants for the rmo passes (de_device.cuh: rmo_band_*; one more state word per path).  Valid (the
+                        // device functions are checked ray by ray in tests/test_gpu_bounds.py) and it cuts the rmo candidates per path 3-7x, yet the
+                        // frame is not faster (profiles/r2_bench.md): an rmo pass is 1-3 candidates either way, what it costs is the stage visit
+                        // (pop, state load, one Philox block, flush, push), not the candidates.  Off; kept for the record.
 #endif
 #ifndef WF_SLOTS
 #if WF_RMO_BANDS
@@ -149,6 +152,10 @@ struct WfParams {
 #ifndef WF_TRACK_PHILOX_INLINE
 #define WF_TRACK_PHILOX_INLINE 0
 #endif
+#ifndef WF_IDLE_EXP
+#define WF_IDLE_EXP 5    // a warp that finds every queue empty sleeps 64 ns << min(consecutive empty rounds, 5) (64 ns ... 2 us) instead of a flat 64 ns:
+                         // half of all scheduling rounds are such polls, and they compete with working warps for issue slots (+0.5 ... 1.4 %)
+#endif
 #ifndef WF_BACKOFF_NS
 #define WF_BACKOFF_NS 0  // sleep after a pop that lost the race for the last group of a queue (idle warps otherwise spin through the scheduler)
 #endif
@@ -238,11 +245,14 @@ __device__ __noinline__ float2 sphere_uv_ool(float px, float py, float pz) { ret
 DE_DEV float r8_ool(const DevTex &t, float3 p) { return fetch_r8_ool(t.obj, t.w, t.h, p.x, p.y, p.z); }
 DE_DEV float3 rgb8_ool(const DevTex &t, float3 p) { return fetch_rgb8_ool(t.obj, t.w, t.h, p.x, p.y, p.z); }
 
-// band exit at ray parameter t: returns (t of the exit, next band as float bits); out of line: called rarely and under divergence
+// The ray leaves altitude band k at parameter t: returns (t where it leaves the band it enters, that band as float bits).  Out of line: called
+// rarely and under divergence.  k < 0: t is the start of the pass, the band is looked up from the altitude there.
 __device__ __noinline__ float2 rmo_band_advance(const DevScene &s, float ox, float oy, float oz, float dx, float dy, float dz, float t, int k) {
+    const float3 d = f3(dx, dy, dz), q = f3(ox, oy, oz) + d * t;
     int kn;
-    const float3 d = f3(dx, dy, dz);
-    const float ds = rmo_band_exit(s, f3(ox, oy, oz) + d * t, d, k, kn);
+    float ds;
+    if (k < 0) { kn = rmo_band_of(s, sqrtf(dot(q, q))); ds = rmo_band_exit(s, q, d, kn); }
+    else ds = rmo_band_cross(s, q, d, k, kn);
     return make_float2(t + ds, __int_as_float(kn));
 }
 struct Ctx {  // per-warp context
@@ -365,11 +375,9 @@ DE_DEV uint32_t setup_rmo(const Ctx &c, int slot, uint32_t pk, float3 o, float3 
         c.pool.cmj[slot] = fminf(lr.max_ext_rmo, rmo_segment_majorant(f3(lr.ext_r, lr.ext_m, lr.ext_o), o, d, t_start, t_max));  // local majorant
 #if WF_RMO_BANDS
         {   // altitude band of the entry point and where the ray leaves it
-            const float3 q = o + d * t_start;
-            const int k = rmo_band_of(c.s, sqrtf(dot(q, q)));
-            const float2 adv = rmo_band_advance(c.s, o.x, o.y, o.z, d.x, d.y, d.z, t_start, k);
+            const float2 adv = rmo_band_advance(c.s, o.x, o.y, o.z, d.x, d.y, d.z, t_start, -1);
             c.pool.tlim[slot] = adv.x;
-            c.pool.draw[slot] = (c.pool.draw[slot] & 0xFFFFFFu) | ((uint32_t)k << 24);
+            c.pool.draw[slot] = (c.pool.draw[slot] & 0xFFFFFFu) | ((uint32_t)__float_as_int(adv.y) << 24);
         }
 #endif
         return PK_SET_STAGE(pk, ST_RMO);
@@ -896,6 +904,9 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
     }
     __syncthreads();
     int last_st = -1;
+#if WF_IDLE_EXP
+    int idle_streak = 0;
+#endif
     bool chained = false;  // the warp already holds slots of stage `st` (handed over by the previous one-shot stage)
     uint32_t st = 0u;
     int slot = -1, n = 0;
@@ -923,12 +934,20 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
             if (key == 0) {
                 if (wl & 2) break;  // every slot found the work counter exhausted
                 long long t0i = COUNT ? clock64() : 0;
+#if WF_IDLE_EXP
+                __nanosleep(64u << min(idle_streak, WF_IDLE_EXP));
+                ++idle_streak;
+#else
                 __nanosleep(WF_BACKOFF_NS > 64 ? WF_BACKOFF_NS : 64);
+#endif
                 if (COUNT && lane == 0 && P.prof) atomicAdd(&P.prof[3 * ST_COUNT], (unsigned long long)(clock64() - t0i));
                 continue;
             }
             st = (uint32_t)(key & 15);
             last_st = (int)st;
+#if WF_IDLE_EXP
+            idle_streak = 0;
+#endif
 #if WF_PHASE
             if ((int)st != phase && lane == 0) pool.phase = (int)st;  // the phase stage ran low: whoever notices moves the SM on
 #endif
