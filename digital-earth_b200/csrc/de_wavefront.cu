@@ -55,6 +55,11 @@ namespace de_fast {
 #ifndef WF_STICKY
 #define WF_STICKY 64
 #endif
+#ifndef WF_CYCLIC
+#define WF_CYCLIC 0  // 1: when the phase stage runs out of full groups the SM moves on to the NEXT stage in dataflow order that has one (NEW, SDF,
+                     // SDF_DONE, RMO, RMO_DONE, CLOUD, EVENT, SURFACE, NEE_DONE, ...) instead of the fullest queue: the pool's paths then travel
+                     // as a wave and the warps of the SM sit on a few adjacent stage bodies (instruction cache, profiles/r2_bench.md)
+#endif
 #ifndef WF_MIN_FRAC8
 #define WF_MIN_FRAC8 6   // ... or this many eighths of the lanes the burst started with
 #endif
@@ -107,6 +112,7 @@ struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
     int q_avail[ST_COUNT];
     int retired;     // slots that found no more work
     int phase;       // SM-wide preferred stage (WF_PHASE)
+    int last_visit;  // counting build: stage of the SM's latest visit
     int work_left;
     unsigned int n_chunks;  // work units of this launch: tiles x samples x 4 quarter-tiles
     unsigned int claimed;   // chunks this CTA claimed (timeline only)
@@ -152,6 +158,17 @@ struct WfParams {
 #ifndef WF_TRACK_PHILOX_INLINE
 #define WF_TRACK_PHILOX_INLINE 0
 #endif
+#ifndef WF_FUSE_RMO
+#define WF_FUSE_RMO 0    // ST_SDF_DONE also runs the FIRST trip (one Philox block, two candidates) of the rmo pass it sets up and, when that ends the
+                         // pass (it usually does: with the segment majorant an rmo pass averages ~2 candidates), the ST_RMO_DONE transition as well:
+                         // SDF_DONE -> RMO -> RMO_DONE collapses into one stage visit for most rays (two pops, pushes and state round trips less);
+                         // the NEE ray of a scatter event enters through the same stage.  The random stream is untouched (a pass starts on a block
+                         // boundary, a trip is one block), so the paths are the same paths.  profiles/r2_bench.md
+#endif
+#ifndef WF_FUSE_CLOUD
+#define WF_FUSE_CLOUD 0  // the ST_RMO_DONE transition also runs the first trip of the cloud pass it sets up (same idea as WF_FUSE_RMO)
+#endif
+static_assert(!(WF_FUSE_RMO && WF_RMO_BANDS), "the fused first trip does not walk altitude bands");
 #ifndef WF_IDLE_EXP
 #define WF_IDLE_EXP 5    // a warp that finds every queue empty sleeps 64 ns << min(consecutive empty rounds, 5) (64 ns ... 2 us) instead of a flat 64 ns:
                          // half of all scheduling rounds are such polls, and they compete with working warps for issue slots (+0.5 ... 1.4 %)
@@ -413,9 +430,63 @@ DE_DEV uint32_t begin_segment(const Ctx &c, int slot, uint32_t pk, float3 o, flo
     return setup_sdf(c, slot, pk, o, d, 0u);
 }
 
+#if WF_FUSE_RMO
+// First trip of an rmo pass (burst_track's loop body, IS_CLOUD = false, for a pass set up a moment ago): one Philox block, two collision
+// candidates.  Returns the pk of ST_RMO_DONE when the pass ended, of ST_RMO (state stored for the loop stage) when it needs more trips.
+template <bool COUNT> DE_DEV uint32_t rmo_first_trip(const Ctx &c, int slot, uint32_t pk, float3 o, float3 d) {
+    const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
+    const float3 ext = f3(lr.ext_r, lr.ext_m, lr.ext_o);
+    const float inv_max = 1.0f / c.pool.cmj[slot], tmax = c.pool.tmax[slot];
+    float t = c.pool.t[slot], T = 1.0f;
+    const bool ratio = (pk & PK_RATIO) != 0u;
+    const uint32_t blk = ((c.pool.draw[slot] & 0xFFFFFFu) + 3u) >> 2;
+    const uint4 rb = philox_block(c.P.seed, c.pool.pix[slot], c.pool.sample[slot], PK_SC(pk) + 1u, blk);
+    bool done = false;
+    uint32_t ev = 0u, id = 0u, draw_after = 0u;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        t -= __logf(u32_to_unit(h ? rb.z : rb.x)) * inv_max;
+        const float3 pos = o + d * t;
+        if (t >= tmax) { done = true; draw_after = 4u * blk + 2u * h + 1u; break; }
+        DE_COUNT(c.cn, C_RMO);
+        const float3 dens = get_density(get_elevation(pos));
+        const float es0 = ext.x * dens.x, es1 = ext.y * dens.y, es2 = ext.z * dens.z, sum = (es0 + es1) + es2;
+        if (ratio) {
+            T *= 1.0f - sum * inv_max;
+            if (T < 1e-5f) { done = true; draw_after = 4u * blk + 2u * h + 2u; break; }
+        } else {
+            const float rand = u32_to_unit(h ? rb.w : rb.y);
+            if (rand < sum * inv_max) {
+                float cmf = es0;
+                if (!(rand < cmf * inv_max)) {
+                    id = 1u; cmf += es1;
+                    if (!(rand < cmf * inv_max)) { id = 2u; cmf += es2; if (!(rand < cmf * inv_max)) id = 3u; }
+                }
+                ev = 1u; done = true; draw_after = 4u * blk + 2u * h + 3u;
+                break;
+            }
+        }
+    }
+    if (!done) {  // the loop stage carries on with the next block
+        c.pool.t[slot] = t;
+        if (ratio) c.pool.aux[slot] = T;
+        store_draw(c, slot, 4u * (blk + 1u), 0u);
+        return pk;
+    }
+    store_draw(c, slot, draw_after, 0u);
+    if (ratio) { c.pool.aux[slot] = T; return PK_SET_STAGE(pk, ST_RMO_DONE); }
+    pk = PK_SET_RMO_EV(pk, ev);
+    pk = PK_SET_RMO_ID(pk, id);
+    c.pool.aux[slot] = t;
+    if (ev) c.pool.nb[slot] = __uint_as_float(draw_after - 1u);
+    return PK_SET_STAGE(pk, ST_RMO_DONE);
+}
+#endif
+template <bool COUNT> DE_DEV uint32_t rmo_done_body(const Ctx &c, int slot, uint32_t pk, float3 o, float3 d);
 // ST_SDF_DONE: what follows intersect_land -- main ray: sample_interaction; shadow ray: visibility +
-// sample_transmittance (pathtracer.py:422-430).  t[slot] holds the intersection distance.
-DE_DEV uint32_t stage_sdf_done(Ctx &c, int slot) {
+// sample_transmittance (pathtracer.py:422-430).  t[slot] holds the intersection distance.  (WF_FUSE_RMO: the NEE ray of a scatter
+// event arrives here as a shadow ray that found nothing, t = -1.)
+template <bool COUNT> DE_DEV uint32_t stage_sdf_done(Ctx &c, int slot) {
     uint32_t pk = c.pool.pk[slot];
     float3 o = ld_o(c, slot), d = ld_d(c, slot);
     float isect = c.pool.t[slot];
@@ -427,15 +498,20 @@ DE_DEV uint32_t stage_sdf_done(Ctx &c, int slot) {
         pk &= ~PK_SHADOW;
     }
     c.pool.isect[slot] = isect;
+#if WF_FUSE_RMO
+    pk = setup_rmo(c, slot, pk, o, d, shadow);
+    if (PK_STAGE(pk) == ST_RMO) pk = rmo_first_trip<COUNT>(c, slot, pk, o, d);
+    if (PK_STAGE(pk) == ST_RMO_DONE) pk = rmo_done_body<COUNT>(c, slot, pk, o, d);
+    return pk;
+#else
     return setup_rmo(c, slot, pk, o, d, shadow);
+#endif
 }
 // ST_RMO_DONE: between the rmo pass and the cloud pass of either tracker.  Delta tracking
 // (sample_interaction, pathtracer.py:189-207) enters the shell only if the rmo pass found no collision
 // before it; ratio tracking (sample_transmittance, :229-231) always does.  One copy of the cloud-bound
 // code serves both (instruction cache).
-DE_DEV uint32_t stage_rmo_done(Ctx &c, int slot) {
-    uint32_t pk = c.pool.pk[slot];
-    float3 o = ld_o(c, slot), d = ld_d(c, slot);
+template <bool COUNT> DE_DEV uint32_t rmo_done_body(const Ctx &c, int slot, uint32_t pk, float3 o, float3 d) {
     const bool ratio = (pk & PK_RATIO) != 0u;
     float ts, tm;
     intersect_cloud_limits(o, d, c.pool.isect[slot], ts, tm);
@@ -446,13 +522,58 @@ DE_DEV uint32_t stage_rmo_done(Ctx &c, int slot) {
     if (enter) {
         const float bound = cloud_pass_setup(c.s, o, d, ts, tm);  // local majorant; the pass ends at the top of the local cloud layer
         if (bound > 0.0f) {
-            c.pool.t[slot] = ts; c.pool.tmax[slot] = tm; c.pool.cmj[slot] = bound;
+            c.pool.tmax[slot] = tm; c.pool.cmj[slot] = bound;
+#if WF_FUSE_CLOUD
+            {   // first trip of the pass (burst_track's loop body, IS_CLOUD = true)
+                const float ext_cloud = cloud_ext_of(PK_SC(pk)), inv_max = 1.0f / (ext_cloud * bound);
+                float t = ts, T = rmo_t;
+                const uint32_t blk = ((c.pool.draw[slot] & 0xFFFFFFu) + 3u) >> 2;
+                const uint4 rb = philox_block(c.P.seed, c.pool.pix[slot], c.pool.sample[slot], PK_SC(pk) + 1u, blk);
+                bool done = false;
+                uint32_t ev = 0u, draw_after = 0u;
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    t -= __logf(u32_to_unit(h ? rb.z : rb.x)) * inv_max;
+                    const float3 pos = o + d * t;
+                    if (t >= tm) { done = true; draw_after = 4u * blk + 2u * h + 1u; break; }
+                    DE_COUNT(c.cn, C_CLOUD);
+                    float r2 = dot(pos, pos), inv_r = rsqrtf(r2), r = r2 * inv_r, dens = 0.0f;
+                    if (r > kCloudsLower && r < kCloudsUpper) {
+                        DE_COUNT(c.cn, C_TEX);
+                        float hgt = (r - kCloudsLower) * (1.0f / kCloudsThickness);
+                        float cl = sample_sphere_r8_inv(c.s.tex[3], pos, inv_r);
+                        dens = (hgt - 0.2f < cl * 0.8f && 0.2f - hgt < cl * 0.2f) ? fmaxf(cl, 0.4f) : 0.0f;
+                    }
+                    const float sum = ext_cloud * (dens * kCloudsDensity);
+                    if (ratio) {
+                        T *= 1.0f - sum * inv_max;
+                        if (T < 1e-5f) { done = true; draw_after = 4u * blk + 2u * h + 2u; break; }
+                    } else if (u32_to_unit(h ? rb.w : rb.y) < sum * inv_max) { ev = 1u; done = true; draw_after = 4u * blk + 2u * h + 3u; break; }
+                }
+                if (done) {
+                    store_draw(c, slot, draw_after, 0u);
+                    if (ratio) { c.pool.aux[slot] = T; return PK_SET_STAGE(pk, ST_NEE_DONE); }
+                    if (ev > 0u && (t < rmo_t || rmo_ev == 0u)) {
+                        c.pool.nb[slot] = __uint_as_float(draw_after - 1u);
+                        return finish_interaction(c, slot, pk, 1u, t, kCloud);
+                    }
+                    return finish_interaction(c, slot, pk, rmo_ev, rmo_t, PK_RMO_ID(pk));
+                }
+                c.pool.t[slot] = t;
+                if (ratio) c.pool.aux[slot] = T;
+                store_draw(c, slot, 4u * (blk + 1u), 0u);
+                return PK_SET_STAGE(pk, ST_CLOUD);
+            }
+#else
+            c.pool.t[slot] = ts;
             return PK_SET_STAGE(pk, ST_CLOUD);  // PK_RATIO stays as it is
+#endif
         }
     }
     if (ratio) return PK_SET_STAGE(pk, ST_NEE_DONE);
     return finish_interaction(c, slot, pk, rmo_ev, rmo_t, PK_RMO_ID(pk));
 }
+template <bool COUNT> DE_DEV uint32_t stage_rmo_done(Ctx &c, int slot) { return rmo_done_body<COUNT>(c, slot, c.pool.pk[slot], ld_o(c, slot), ld_d(c, slot)); }
 
 // ------------------------------------------------------------------ path start / end
 // ST_NEW (free slots): Renderer.render prologue for one sample (renderer.py:305-314).  Called with
@@ -785,8 +906,13 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
         pk = PK_SET_ID(pk, id) & ~PK_SURFACE;
         store_draw(c, slot, rng.draw, 0u);
         if (blocked) { c.pool.aux[slot] = 0.0f; return PK_SET_STAGE(pk, ST_NEE_DONE); }
+#if WF_FUSE_RMO
+        c.pool.t[slot] = -1.0f;  // "a shadow ray that found nothing": ST_SDF_DONE sets isect = -1, ratio tracking, and runs the pass's first trip
+        return PK_SET_STAGE(pk | PK_SHADOW, ST_SDF_DONE);
+#else
         c.pool.isect[slot] = -1.0f;
         return setup_rmo(c, slot, pk, ipos, light_dir, true);
+#endif
     }
     // surface hit: shading is a long body of its own (four height fetches, four material maps, the BRDF) that a
     // fifth of the events need -- it runs as stage ST_SURFACE over a full group instead of a few lanes of this one
@@ -897,7 +1023,7 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         pool.q_avail[threadIdx.x] = threadIdx.x == ST_NEW ? WF_SLOTS : 0;
     }
     if (threadIdx.x == 0) {
-        pool.retired = 0; pool.work_left = 1; pool.phase = 0; pool.claimed = 0u; pool.t_exhaust = 0ull; pool.t_few = 0ull;
+        pool.retired = 0; pool.work_left = 1; pool.phase = 0; pool.last_visit = -1; pool.claimed = 0u; pool.t_exhaust = 0ull; pool.t_few = 0ull;
         for (int k = 0; k < (int)ST_COUNT; ++k) { pool.dr_visits[k] = 0u; pool.dr_slots[k] = 0u; }
         pool.n_chunks = __ldg(P.n_tiles) * (unsigned)P.n_spp * 4u;
         if (COUNT && P.timeline) atomicMin(&P.timeline[0], globaltimer_ns());
@@ -924,11 +1050,20 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
             // plain fullest-queue policy: stage affinity per sub-partition and role-specialised warps were
             // both measured slower (profiles/r1_wavefront.md, "scheduling experiments")
             int key = av > 0 ? (av << 4) | lane : 0;
+#if WF_CYCLIC
+            {   // stage -> position in the dataflow cycle (nibble table), distance from the phase stage; full groups rank by that distance
+                const unsigned long long kOrd = 0x786425310ULL;
+                int dist = (int)((kOrd >> (4 * (lane < (int)ST_COUNT ? lane : 0))) & 15ull) - (int)((kOrd >> (4 * phase)) & 15ull);
+                if (dist < 0) dist += (int)ST_COUNT;
+                if (av >= 32) key = (1 << 20) | (((int)ST_COUNT - dist) << 16) | lane;
+            }
+#else
 #if WF_STICKY
             if (lane == last_st && av >= WF_STICKY) key += 1 << 20;  // stay on the stage whose code is warm while it has a full group
 #endif
 #if WF_PHASE
             if (lane == phase && av >= WF_PHASE) key += 1 << 21;     // SM-wide phase: everybody on the same body while it lasts
+#endif
 #endif
             key = __reduce_max_sync(full, key);
             if (key == 0) {
@@ -997,8 +1132,8 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
                     continue;
                 }
             } else if (has) {
-                if (st == ST_SDF_DONE) npk = stage_sdf_done(c, slot);
-                else if (st == ST_RMO_DONE) npk = stage_rmo_done(c, slot);
+                if (st == ST_SDF_DONE) npk = stage_sdf_done<COUNT>(c, slot);
+                else if (st == ST_RMO_DONE) npk = stage_rmo_done<COUNT>(c, slot);
                 else if (st == ST_EVENT) npk = stage_event<COUNT>(c, slot);
                 else if (st == ST_SURFACE) npk = stage_surface<COUNT>(c, slot);
                 else npk = stage_nee_done<COUNT>(c, slot);
@@ -1042,6 +1177,7 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
         }
         if (COUNT && P.timeline && lane == 0 && !work_left) { atomicAdd(&pool.dr_visits[st_run], 1u); atomicAdd(&pool.dr_slots[st_run], (unsigned)n_run); }
         if (COUNT && lane == 0 && P.prof) {
+            if (atomicExch(&pool.last_visit, (int)st_run) != (int)st_run) atomicAdd(&P.prof[3 * ST_COUNT + 1], 1ull);  // the SM changed stage body
             atomicAdd(&P.prof[3 * st_run], (unsigned long long)(clock64() - t0s));
             atomicAdd(&P.prof[3 * st_run + 1], 1ull);
             atomicAdd(&P.prof[3 * st_run + 2], (unsigned long long)n_run);

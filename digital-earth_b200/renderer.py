@@ -216,6 +216,7 @@ class Renderer:
         names = ("NEW", "SDF", "RMO", "CLOUD", "SDF_DONE", "RMO_DONE", "EVENT", "NEE_DONE", "SURFACE")
         out = {n: tuple(int(x) for x in buf[3 * i:3 * i + 3]) for i, n in enumerate(names)}
         out["IDLE"] = (int(buf[3 * len(names)]), 0, 0)
+        out["SWITCHES"] = (0, int(buf[3 * len(names) + 1]), 0)  # visits whose stage differs from the SM's previous visit
         return out
 
     def _bind_stream(self):

@@ -52,5 +52,8 @@ for scene in a.scenes.split(","):
         print(line, flush=True)
         if a.count and mode == 'wavefront' and prof:
             tot = sum(v[0] for v in prof.values())
-            print('    stage share of warp cycles: ' + '  '.join('%s %.1f%% (%.1f slots/visit)' % (k, 100.0 * v[0] / tot, v[2] / max(v[1], 1)) for k, v in prof.items()), flush=True)
+            sw = prof.pop('SWITCHES', (0, 0, 0))[1]
+            visits = sum(v[1] for v in prof.values())
+            print('    stage share of warp cycles: ' + '  '.join('%s %.1f%% (%.1f slots/visit)' % (k, 100.0 * v[0] / tot, v[2] / max(v[1], 1)) for k, v in prof.items())
+                  + '  | %.1f%% of %d visits change the SM\'s stage body' % (100.0 * sw / max(visits, 1), visits), flush=True)
     r.close()

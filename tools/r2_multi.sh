@@ -7,7 +7,7 @@ O=gpurun_out/r2m$N; mkdir -p $O
 P=29600
 run() {  # name, args...
   name=$1; shift; P=$((P+1))
-  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N "$@" > $O/$name.json 2> $O/$name.err
+  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N --no-cpu-baseline "$@" > $O/$name.json 2> $O/$name.err
   echo "$name rc=$? $(cut -c1-180 $O/$name.json)"
 }
 run apollo_spp --steps 3 --warmup 3
