@@ -280,11 +280,18 @@ DE_DEV float3 sample_sphere_rgb8(const DevTex &t, float3 pos) { float2 uv = sphe
 // pi that stay away from the poles), latitude leaves the endpoint range by at most ~theta^2/8 * tan(lat).  The
 // bound is the maximum of the dilated coarse map over that lat-long box; 1.0 (no information)
 // whenever the box is unsafe (date-line crossing, polar caps, long arcs, too many cells).
+#if defined(DE_WF_SHRINK) && DE_WF_SHRINK
+__device__ __noinline__ float2 sphere_uv_ool(float px, float py, float pz);  // de_wavefront.cu: one shared copy of the equirect mapping (code size)
+#define DE_CMAX_UV(p) sphere_uv_ool((p).x, (p).y, (p).z)
+#else
+#define DE_CMAX_UV(p) sphere_uv(p)
+#endif
 DE_DEV float cloud_segment_cmax(const DevScene &s, float3 o, float3 d, float ts, float tm) {
     if (!s.cloud_max) return 1.0f;
     float theta = (tm - ts) * (1.0f / 6375000.0f);
     if (!(theta < 0.25f)) return 1.0f;
-    float2 a = sphere_uv(o + d * ts), b = sphere_uv(o + d * tm);
+    const float3 pa = o + d * ts, pb = o + d * tm;
+    float2 a = DE_CMAX_UV(pa), b = DE_CMAX_UV(pb);
     if (fabsf(a.x - b.x) > 0.4f) return 1.0f;
     // latitude: sin(lat) is a sinusoid of amplitude <= 1 along the arc, so it leaves the end points' range by at most
     // 1 - cos(theta/2) <= theta^2/8; inside |lat| <= 81 deg (which the coarse test with the trivial bound theta/2 guarantees)

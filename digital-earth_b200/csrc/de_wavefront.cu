@@ -21,6 +21,11 @@
 // The random stream of a path is the contract of include/de_api.h (Philox key (seed,pixel), counter
 // (sample,bounce,slot>>2)), so a pixel's samples are the same paths in every integrator flavour.
 #define DE_TEX_OBJ_ONLY 1
+#ifndef WF_SHRINK
+#define WF_SHRINK 0  // 1: one shared out-of-line copy of the equirect mapping inside the cloud bound, of the rmo segment majorant (2 inlined copies) and
+                     // of the terrain-march prologue (3 inlined copies): the kernel is bound by instruction fetch (profiles/r2_bench.md)
+#endif
+#define DE_WF_SHRINK WF_SHRINK
 #include "de_integrator.cuh"
 #include "de_launch.h"
 #include "de_wavefront.h"
@@ -33,8 +38,17 @@ namespace de_fast {
                         // frame is not faster (profiles/r2_bench.md): an rmo pass is 1-3 candidates either way, what it costs is the stage visit
                         // (pop, state load, one Philox block, flush, push), not the candidates.  Off; kept for the record.
 #endif
+#ifndef WF_COLD
+#define WF_COLD 0      // 1: the 13 words of a path's state that only the shading stages touch (throughput, radiance, NEE factors, main direction,
+                       // normal, material) live in global memory (64 B per slot, L2-resident: 148 x 2464 x 64 B = 23 MB) instead of shared
+                       // memory; the pool then holds 2464 paths of 16 hot words instead of 1728 of 28.  Why: the kernel is bound by
+                       // instruction fetch (profiles/r2_bench.md) and how often a stage body is re-fetched falls with the number of paths
+                       // WAITING in the stage queues (pool size minus the 32 x 32 in flight): 750 -> 1480.
+#endif
 #ifndef WF_SLOTS
-#if WF_RMO_BANDS
+#if WF_COLD
+#define WF_SLOTS 2464
+#elif WF_RMO_BANDS
 #define WF_SLOTS 1664  // path states per CTA (one CTA per SM): 188 KB of state (29 words each) + 36 KB of queues
 #else
 #define WF_SLOTS 1728  // 28 words each
@@ -66,8 +80,11 @@ namespace de_fast {
 #ifndef WF_REFILL_MIN
 #define WF_REFILL_MIN 10 // idle lanes that trigger a mid-burst refill
 #endif
-constexpr int WF_RING = 2048;  // ring capacity per stage queue (power of two >= WF_SLOTS)
-static_assert(WF_RING >= WF_SLOTS && (WF_RING & (WF_RING - 1)) == 0 && WF_SLOTS < 2048, "ring / slot-id encoding");
+// ring capacity per stage queue (power of two > WF_SLOTS); an entry is slot | lap tag << WF_SLOT_BITS in 16 bits
+constexpr int WF_SLOT_BITS = WF_SLOTS < 2048 ? 11 : 12;
+constexpr int WF_RING = 1 << WF_SLOT_BITS;
+constexpr unsigned WF_TAG_MASK = (1u << (16 - WF_SLOT_BITS)) - 1u;
+static_assert(WF_SLOTS < WF_RING && WF_SLOTS % 32 == 0, "ring / slot-id encoding");
 
 // Stages.  Loop stages (SDF, RMO, CLOUD) run bursts of a small loop body; the others are one-shot
 // bodies executed converged over up to 32 slots.  A loop body never runs transition code.
@@ -96,12 +113,16 @@ DE_DEV uint32_t pk_set(uint32_t p, int shift, uint32_t mask, uint32_t v) { retur
 
 struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
     float ox[WF_SLOTS], oy[WF_SLOTS], oz[WF_SLOTS], dx[WF_SLOTS], dy[WF_SLOTS], dz[WF_SLOTS];
-    float thr[WF_SLOTS], L[WF_SLOTS];
     uint32_t pix[WF_SLOTS], sample[WF_SLOTS], pk[WF_SLOTS], draw[WF_SLOTS];  // draw: rng slot index [0:24) | sdf iteration [24:32)
     float t[WF_SLOTS], tmax[WF_SLOTS], aux[WF_SLOTS], isect[WF_SLOTS];       // aux: rmo_t (delta) or transmittance (ratio)
+#if WF_COLD
+    uint32_t dsl[WF_SLOTS];                                                   // rng slot of the scatter / absorb decision of the pending collision
+#else
+    float thr[WF_SLOTS], L[WF_SLOTS];
     float mdx[WF_SLOTS], mdy[WF_SLOTS], mdz[WF_SLOTS];                        // main ray direction while the NEE ray is tracked
     float nx[WF_SLOTS], ny[WF_SLOTS], nz[WF_SLOTS], m0[WF_SLOTS], m1[WF_SLOTS], m2[WF_SLOTS];  // surface normal, albedo, ocean, bathymetry
     float na[WF_SLOTS], nb[WF_SLOTS];                                         // NEE factors: phase | brdf, n.l (nb doubles as the decision-slot word)
+#endif
     float cmj[WF_SLOTS];                                                      // tracking pass: local majorant (cloud: density bound; rmo: sigma.rho bound of the whole segment)
 #if WF_RMO_BANDS
     float tlim[WF_SLOTS];                                                     // rmo pass: where the ray leaves its current altitude band (draw[24:32) holds the band)
@@ -123,6 +144,7 @@ struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
 
 struct WfParams {
     float *accum;
+    float4 *cold;        // WF_COLD: [gridDim.x][WF_SLOTS][4] shading state of the paths in flight
     float *accum2;       // optional per-pixel second moments (sum of squared contributions), or nullptr
     unsigned int *next;  // global work counter (units of 32 paths)
     const unsigned int *tile_list;  // film tiles this kernel renders (k_classify_tiles: everything that is not pure space)
@@ -259,6 +281,21 @@ __device__ __noinline__ float4 phase_sample_ool(float dx, float dy, float dz, in
     return make_float4(d.x, d.y, d.z, pdp);
 }
 __device__ __noinline__ float2 sphere_uv_ool(float px, float py, float pz) { return sphere_uv(f3(px, py, pz)); }
+#if WF_SHRINK
+__device__ __noinline__ float rmo_majorant_ool(float ex, float em, float eo, float ox, float oy, float oz, float dx, float dy, float dz, float ts, float tm) {
+    return rmo_segment_majorant(f3(ex, em, eo), f3(ox, oy, oz), f3(dx, dy, dz), ts, tm);
+}
+// intersect_land prologue (pathtracer.py:29-35): where the march starts, or -1 when the ray surely misses the terrain
+__device__ __noinline__ float sdf_start_ool(float ox, float oy, float oz, float dx, float dy, float dz, float scale) {
+    const float3 o = f3(ox, oy, oz), d = f3(dx, dy, dz);
+    float ray_dist = 0.0f;
+    const float2 rd = rsi(o, d, kAtmosUpper);
+    if (rd.x > 0.0f) ray_dist = rd.x;
+    const float3 p = o + d * ray_dist;
+    if (land_surely_missed(p, d, ray_dist, scale)) return -1.0f;
+    return ray_dist + skip_to_terrain_top(p, d, ray_dist, scale);
+}
+#endif
 DE_DEV float r8_ool(const DevTex &t, float3 p) { return fetch_r8_ool(t.obj, t.w, t.h, p.x, p.y, p.z); }
 DE_DEV float3 rgb8_ool(const DevTex &t, float3 p) { return fetch_rgb8_ool(t.obj, t.w, t.h, p.x, p.y, p.z); }
 
@@ -279,6 +316,7 @@ struct Ctx {  // per-warp context
     WarpPool &pool;
     Counters &cn;
     int lane;
+    float4 *cold;  // this CTA's part of WfParams::cold
 };
 
 // ---- stage queues -------------------------------------------------------------------------
@@ -288,7 +326,7 @@ struct Ctx {  // per-warp context
 DE_DEV void q_push(WarpPool &p, uint32_t st, int slot) {
     unsigned int pos = atomicAdd(&p.q_tail[st], 1u);
     volatile uint16_t *r = p.ring[st];
-    r[pos & (WF_RING - 1)] = (uint16_t)((unsigned)slot | (((pos / WF_RING) & 31u) << 11));
+    r[pos & (WF_RING - 1)] = (uint16_t)((unsigned)slot | (((pos / WF_RING) & WF_TAG_MASK) << WF_SLOT_BITS));
     __threadfence_block();
     atomicAdd(&p.q_avail[st], 1);
 }
@@ -308,7 +346,7 @@ void q_push_group(WarpPool &p, uint32_t st, int slot, unsigned mask, int lane) {
     base = __shfl_sync(mask, base, leader);
     unsigned int pos = base + (unsigned)__popc(mask & ((1u << lane) - 1u));
     volatile uint16_t *r = p.ring[st];
-    r[pos & (WF_RING - 1)] = (uint16_t)((unsigned)slot | (((pos / WF_RING) & 31u) << 11));
+    r[pos & (WF_RING - 1)] = (uint16_t)((unsigned)slot | (((pos / WF_RING) & WF_TAG_MASK) << WF_SLOT_BITS));
     __threadfence_block();
     __syncwarp(mask);
     if (lane == leader) atomicAdd(&p.q_avail[st], n);
@@ -341,11 +379,11 @@ __device__ __noinline__ int2 q_pop2(WarpPool &p, uint32_t st, int want, int lane
     slot = -1;
     if (lane < n) {
         unsigned int pos = base + (unsigned)lane;
-        const unsigned tag = (pos / WF_RING) & 31u;
+        const unsigned tag = (pos / WF_RING) & WF_TAG_MASK;
         volatile uint16_t *r = p.ring[st];
         unsigned e;
-        do { e = r[pos & (WF_RING - 1)]; } while ((e >> 11) != tag);
-        slot = (int)(e & 2047u);
+        do { e = r[pos & (WF_RING - 1)]; } while ((e >> WF_SLOT_BITS) != tag);
+        slot = (int)(e & (unsigned)(WF_RING - 1));
     }
     return make_int2(n, slot);
 }
@@ -366,6 +404,34 @@ DE_DEV float3 ld_o(const Ctx &c, int s) { return f3(c.pool.ox[s], c.pool.oy[s], 
 DE_DEV float3 ld_d(const Ctx &c, int s) { return f3(c.pool.dx[s], c.pool.dy[s], c.pool.dz[s]); }
 DE_DEV void st_o(const Ctx &c, int s, float3 v) { c.pool.ox[s] = v.x; c.pool.oy[s] = v.y; c.pool.oz[s] = v.z; }
 DE_DEV void st_d(const Ctx &c, int s, float3 v) { c.pool.dx[s] = v.x; c.pool.dy[s] = v.y; c.pool.dz[s] = v.z; }
+// Shading state of a slot: q0 = (throughput, radiance, NEE factor a, NEE factor b), q1 = (main direction, albedo), q2 = (normal | light
+// direction, oceanness), q3 = (bathymetry).  WF_COLD: 64 B per slot in global memory, L2 only (.cg: written by one warp, read by another of the
+// same CTA after a queue hand-over, which carries a __threadfence_block); otherwise the pool's arrays.
+#if WF_COLD
+DE_DEV float4 cold_ld(const Ctx &c, int slot, int q) { return __ldcg(c.cold + slot * 4 + q); }
+DE_DEV void cold_st(const Ctx &c, int slot, int q, float4 v) { __stcg(c.cold + slot * 4 + q, v); }
+DE_DEV void cold_st_thr_L(const Ctx &c, int slot, float thr, float L) { __stcg(reinterpret_cast<float2 *>(c.cold + slot * 4), make_float2(thr, L)); }
+DE_DEV void cold_st_na(const Ctx &c, int slot, float na) { __stcg(reinterpret_cast<float *>(c.cold + slot * 4) + 2, na); }
+DE_DEV float cold_ld_L(const Ctx &c, int slot) { return __ldcg(reinterpret_cast<const float *>(c.cold + slot * 4) + 1); }
+#define WF_DSL(c, slot) (c).pool.dsl[slot]
+#else
+DE_DEV float4 cold_ld(const Ctx &c, int s, int q) {
+    const WarpPool &p = c.pool;
+    return q == 0 ? make_float4(p.thr[s], p.L[s], p.na[s], p.nb[s]) : q == 1 ? make_float4(p.mdx[s], p.mdy[s], p.mdz[s], p.m0[s])
+         : q == 2 ? make_float4(p.nx[s], p.ny[s], p.nz[s], p.m1[s]) : make_float4(p.m2[s], 0.0f, 0.0f, 0.0f);
+}
+DE_DEV void cold_st(const Ctx &c, int s, int q, float4 v) {
+    WarpPool &p = c.pool;
+    if (q == 0) { p.thr[s] = v.x; p.L[s] = v.y; p.na[s] = v.z; p.nb[s] = v.w; }
+    else if (q == 1) { p.mdx[s] = v.x; p.mdy[s] = v.y; p.mdz[s] = v.z; p.m0[s] = v.w; }
+    else if (q == 2) { p.nx[s] = v.x; p.ny[s] = v.y; p.nz[s] = v.z; p.m1[s] = v.w; }
+    else p.m2[s] = v.x;
+}
+DE_DEV void cold_st_thr_L(const Ctx &c, int s, float thr, float L) { c.pool.thr[s] = thr; c.pool.L[s] = L; }
+DE_DEV void cold_st_na(const Ctx &c, int s, float na) { c.pool.na[s] = na; }
+DE_DEV float cold_ld_L(const Ctx &c, int s) { return c.pool.L[s]; }
+#define WF_DSL(c, slot) (*reinterpret_cast<uint32_t *>(&(c).pool.nb[slot]))
+#endif
 DE_DEV float cloud_ext_of(uint32_t sc) { return sc > 9u ? 0.02f : kCloudsExtinct; }  // pathtracer.py:351-352
 
 // ------------------------------------------------------------------ transitions (run converged inside one-shot stages)
@@ -389,7 +455,11 @@ DE_DEV uint32_t setup_rmo(const Ctx &c, int slot, uint32_t pk, float3 o, float3 
     if (t_start < t_max) {
         const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
         c.pool.t[slot] = t_start; c.pool.tmax[slot] = t_max;
+#if WF_SHRINK
+        c.pool.cmj[slot] = fminf(lr.max_ext_rmo, rmo_majorant_ool(lr.ext_r, lr.ext_m, lr.ext_o, o.x, o.y, o.z, d.x, d.y, d.z, t_start, t_max));
+#else
         c.pool.cmj[slot] = fminf(lr.max_ext_rmo, rmo_segment_majorant(f3(lr.ext_r, lr.ext_m, lr.ext_o), o, d, t_start, t_max));  // local majorant
+#endif
 #if WF_RMO_BANDS
         {   // altitude band of the entry point and where the ray leaves it
             const float2 adv = rmo_band_advance(c.s, o.x, o.y, o.z, d.x, d.y, d.z, t_start, -1);
@@ -413,6 +483,12 @@ __device__ __noinline__
 DE_DEV
 #endif
 uint32_t setup_sdf(const Ctx &c, int slot, uint32_t pk, float3 o, float3 d, uint32_t draw) {
+#if WF_SHRINK
+    store_draw(c, slot, draw, 0u);
+    const float t0 = sdf_start_ool(o.x, o.y, o.z, d.x, d.y, d.z, c.s.land_height_scale);
+    c.pool.t[slot] = t0;
+    return PK_SET_STAGE(pk, t0 < 0.0f ? ST_SDF_DONE : ST_SDF);
+#endif
     float ray_dist = 0.0f;
     float2 rd = rsi(o, d, kAtmosUpper);
     if (rd.x > 0.0f) ray_dist = rd.x;
@@ -478,7 +554,7 @@ template <bool COUNT> DE_DEV uint32_t rmo_first_trip(const Ctx &c, int slot, uin
     pk = PK_SET_RMO_EV(pk, ev);
     pk = PK_SET_RMO_ID(pk, id);
     c.pool.aux[slot] = t;
-    if (ev) c.pool.nb[slot] = __uint_as_float(draw_after - 1u);
+    if (ev) WF_DSL(c, slot) = draw_after - 1u;
     return PK_SET_STAGE(pk, ST_RMO_DONE);
 }
 #endif
@@ -554,7 +630,7 @@ template <bool COUNT> DE_DEV uint32_t rmo_done_body(const Ctx &c, int slot, uint
                     store_draw(c, slot, draw_after, 0u);
                     if (ratio) { c.pool.aux[slot] = T; return PK_SET_STAGE(pk, ST_NEE_DONE); }
                     if (ev > 0u && (t < rmo_t || rmo_ev == 0u)) {
-                        c.pool.nb[slot] = __uint_as_float(draw_after - 1u);
+                        WF_DSL(c, slot) = draw_after - 1u;
                         return finish_interaction(c, slot, pk, 1u, t, kCloud);
                     }
                     return finish_interaction(c, slot, pk, rmo_ev, rmo_t, PK_RMO_ID(pk));
@@ -585,7 +661,7 @@ template <bool COUNT> DE_DEV uint32_t stage_rmo_done(Ctx &c, int slot) { return 
 #else
 #define WF_ENDPATH_ATTR DE_DEV
 #endif
-template <bool COUNT> WF_ENDPATH_ATTR uint32_t end_path(Ctx &c, int slot, uint32_t pk, bool primary_miss, float3 dir);
+template <bool COUNT> WF_ENDPATH_ATTR uint32_t end_path(Ctx &c, int slot, uint32_t pk, bool primary_miss, float3 dir, float Lr);
 template <bool COUNT> DE_DEV uint32_t stage_new(Ctx &c, int slot) {
     const unsigned full = 0xFFFFFFFFu;
     const WfParams &P = c.P;
@@ -607,21 +683,20 @@ template <bool COUNT> DE_DEV uint32_t stage_new(Ctx &c, int slot) {
     float xu = rng.next(), xv = rng.next();
     float3 dir = get_cast_dir(c.s, c.dv, (float)px, (float)py, xu, xv);
     c.pool.pix[slot] = rng.key1; c.pool.sample[slot] = rng.sample;
-    c.pool.thr[slot] = 1.0f; c.pool.L[slot] = 0.0f;
     DE_COUNT(c.cn, C_SEGMENTS);
 #if WF_SPACE_SHORTCUT
     // A primary ray that misses the atmosphere shell interacts with nothing (every later test of the
     // segment uses a smaller sphere): it is a primary miss right here (pathtracer.py:441-444,455-466),
     // instead of five queue hops.  rsi keeps the reference's NaN-on-miss behaviour, hence the negation.
-    if (!(rsi(c.s.cam_pos, dir, kAtmosUpper).y >= 0.0f)) return end_path<COUNT>(c, slot, PK_SET_LAM(0u, (uint32_t)bin), true, dir);
+    if (!(rsi(c.s.cam_pos, dir, kAtmosUpper).y >= 0.0f)) return end_path<COUNT>(c, slot, PK_SET_LAM(0u, (uint32_t)bin), true, dir, 0.0f);
 #endif
+    cold_st_thr_L(c, slot, 1.0f, 0.0f);
     st_o(c, slot, c.s.cam_pos); st_d(c, slot, dir);
     return begin_segment(c, slot, PK_SET_LAM(0u, (uint32_t)bin), c.s.cam_pos, dir);
 }
 // pathtracer.py:455-469 + renderer.py:329-330; frees the slot
-template <bool COUNT> WF_ENDPATH_ATTR uint32_t end_path(Ctx &c, int slot, uint32_t pk, bool primary_miss, float3 dir) {
+template <bool COUNT> WF_ENDPATH_ATTR uint32_t end_path(Ctx &c, int slot, uint32_t pk, bool primary_miss, float3 dir, float Lr) {
     const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
-    float Lr = c.pool.L[slot];
     if (primary_miss) {
         if (dot(c.dv.light_dir, dir) > c.dv.sun_cos_angle) Lr += lr.sun_power;
         DE_COUNT(c.cn, C_TEX);
@@ -844,14 +919,14 @@ template <bool COUNT> DE_DEV void burst_track(Ctx &c, int slot, const bool IS_CL
                     uint32_t rmo_ev = PK_RMO_EV(pk);
                     float rmo_t = c.pool.aux[slot];
                     if (ev > 0u && (t < rmo_t || rmo_ev == 0u)) {
-                        c.pool.nb[slot] = __uint_as_float(draw_after - 1u);
+                        WF_DSL(c, slot) = draw_after - 1u;
                         npk = finish_interaction(c, slot, pk, 1u, t, kCloud);
                     } else npk = finish_interaction(c, slot, pk, rmo_ev, rmo_t, PK_RMO_ID(pk));
                 } else {
                     npk = PK_SET_RMO_EV(pk, ev);
                     npk = PK_SET_RMO_ID(npk, id);
                     c.pool.aux[slot] = t;
-                    if (ev) c.pool.nb[slot] = __uint_as_float(draw_after - 1u);
+                    if (ev) WF_DSL(c, slot) = draw_after - 1u;
                     npk = PK_SET_STAGE(npk, ST_RMO_DONE);
                 }
                 c.pool.pk[slot] = npk;
@@ -884,7 +959,7 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
     RngW rng = load_rng(c, slot, pk);
     uint32_t ev = PK_EV(pk), id = PK_ID(pk);
     if (ev) {  // a real collision: scatter or absorb (pathtracer.py:108-111,263-270) from the recorded slot
-        uint32_t ds = __float_as_uint(c.pool.nb[slot]);
+        uint32_t ds = WF_DSL(c, slot);
         uint4 b = philox_block(rng.key0, rng.key1, rng.sample, rng.bounce, ds >> 2);
         uint32_t w = (ds & 3u) == 0u ? b.x : ((ds & 3u) == 1u ? b.y : ((ds & 3u) == 2u ? b.z : b.w));
         float albedo = id == 0u ? 1.0f : (id == 1u ? 0.95f : (id == 2u ? 0.0f : 0.99f));
@@ -896,12 +971,12 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
     const float earth_isect = c.pool.isect[slot];
     const bool absorbed = ev == (uint32_t)kAbsorbEvent;
     if (absorbed || (ev != (uint32_t)kScatterEvent && !(earth_isect > 0.0f)))  // absorbed, or escaped (pathtracer.py:441-444)
-        return end_path<COUNT>(c, slot, pk, !absorbed && sc == 0u, d);
+        return end_path<COUNT>(c, slot, pk, !absorbed && sc == 0u, d, cold_ld_L(c, slot));
     if (ev == (uint32_t)kScatterEvent) {
         float3 ipos = o + d * c.pool.t[slot];
         bool blocked = rsi(ipos, light_dir, kPlanetR).y > 0.0f;
-        c.pool.na[slot] = phase_eval_ool(d.x, d.y, d.z, light_dir.x, light_dir.y, light_dir.z, (int)id, sc > 0u);
-        c.pool.mdx[slot] = d.x; c.pool.mdy[slot] = d.y; c.pool.mdz[slot] = d.z;
+        cold_st_na(c, slot, phase_eval_ool(d.x, d.y, d.z, light_dir.x, light_dir.y, light_dir.z, (int)id, sc > 0u));
+        cold_st(c, slot, 1, make_float4(d.x, d.y, d.z, 0.0f));
         st_o(c, slot, ipos); st_d(c, slot, light_dir);
         pk = PK_SET_ID(pk, id) & ~PK_SURFACE;
         store_draw(c, slot, rng.draw, 0u);
@@ -916,7 +991,7 @@ template <bool COUNT> DE_DEV uint32_t stage_event(Ctx &c, int slot) {
     }
     // surface hit: shading is a long body of its own (four height fetches, four material maps, the BRDF) that a
     // fifth of the events need -- it runs as stage ST_SURFACE over a full group instead of a few lanes of this one
-    c.pool.nx[slot] = light_dir.x; c.pool.ny[slot] = light_dir.y; c.pool.nz[slot] = light_dir.z;
+    cold_st(c, slot, 2, make_float4(light_dir.x, light_dir.y, light_dir.z, 0.0f));
     store_draw(c, slot, rng.draw, 0u);
     return PK_SET_STAGE(pk, ST_SURFACE);
 }
@@ -926,7 +1001,8 @@ template <bool COUNT> DE_DEV uint32_t stage_surface(Ctx &c, int slot) {
     uint32_t pk = c.pool.pk[slot];
     const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
     const float3 o = ld_o(c, slot), d = ld_d(c, slot);
-    const float3 light_dir = f3(c.pool.nx[slot], c.pool.ny[slot], c.pool.nz[slot]);
+    const float4 q2 = cold_ld(c, slot, 2), q0 = cold_ld(c, slot, 0);
+    const float3 light_dir = f3(q2.x, q2.y, q2.z);
     const float earth_isect = c.pool.isect[slot];
     const uint32_t draw = c.pool.draw[slot] & 0xFFFFFFu;
     {
@@ -946,13 +1022,13 @@ template <bool COUNT> DE_DEV uint32_t stage_surface(Ctx &c, int slot) {
         m.bathymetry = tex_r8(c.s.tex[4], muv.x, muv.y);
         m.emissive = tex_r8(c.s.tex[5], muv.x, muv.y);
         float albedo = lr.s2s_valid != 0.0f ? dot(m.albedo_srgb, f3(lr.s2s_r, lr.s2s_g, lr.s2s_b)) : 0.0f;
-        c.pool.L[slot] += c.pool.thr[slot] * m.emissive * lr.nightlights_power;
+        const float L_new = q0.y + q0.x * m.emissive * lr.nightlights_power;
         float3 offset_pos = land_pos * (1.0f + 0.0001f * c.s.land_height_scale / 12000.0f);
         float2 bn = brdf_ool(albedo, m.ocean, m.bathymetry, -d.x, -d.y, -d.z, nrm.x, nrm.y, nrm.z, light_dir.x, light_dir.y, light_dir.z);
-        c.pool.na[slot] = bn.x; c.pool.nb[slot] = bn.y;
-        c.pool.nx[slot] = nrm.x; c.pool.ny[slot] = nrm.y; c.pool.nz[slot] = nrm.z;
-        c.pool.m0[slot] = albedo; c.pool.m1[slot] = m.ocean; c.pool.m2[slot] = m.bathymetry;
-        c.pool.mdx[slot] = d.x; c.pool.mdy[slot] = d.y; c.pool.mdz[slot] = d.z;
+        cold_st(c, slot, 0, make_float4(q0.x, L_new, bn.x, bn.y));
+        cold_st(c, slot, 1, make_float4(d.x, d.y, d.z, albedo));
+        cold_st(c, slot, 2, make_float4(nrm.x, nrm.y, nrm.z, m.ocean));
+        cold_st(c, slot, 3, make_float4(m.bathymetry, 0.0f, 0.0f, 0.0f));
         st_o(c, slot, offset_pos); st_d(c, slot, light_dir);
         pk |= PK_SURFACE | PK_SHADOW;
         return setup_sdf(c, slot, pk, offset_pos, light_dir, draw);
@@ -966,19 +1042,21 @@ template <bool COUNT> DE_DEV uint32_t stage_nee_done(Ctx &c, int slot) {
     const LambdaRow &lr = c.s.lam[PK_LAM(pk)];
     RngW rng = load_rng(c, slot, pk);
     float3 o = ld_o(c, slot);  // interaction position / offset position
-    float3 main_d = f3(c.pool.mdx[slot], c.pool.mdy[slot], c.pool.mdz[slot]);
-    float T = c.pool.aux[slot], thr = c.pool.thr[slot], Lacc = c.pool.L[slot];
+    const float4 q0 = cold_ld(c, slot, 0), q1 = cold_ld(c, slot, 1);
+    float3 main_d = f3(q1.x, q1.y, q1.z);
+    float T = c.pool.aux[slot], thr = q0.x, Lacc = q0.y;
     float3 nd;
     if (pk & PK_SURFACE) {
         float vis = (pk & PK_VIS) ? 1.0f : 0.0f;
-        Lacc += thr * T * vis * lr.sun_irradiance * c.pool.na[slot] * c.pool.nb[slot];
-        float3 nrm = f3(c.pool.nx[slot], c.pool.ny[slot], c.pool.nz[slot]);
+        const float4 q2 = cold_ld(c, slot, 2), q3 = cold_ld(c, slot, 3);
+        Lacc += thr * T * vis * lr.sun_irradiance * q0.z * q0.w;
+        float3 nrm = f3(q2.x, q2.y, q2.z);
         rng.align();
         nd = sample_hemisphere_cosine_weighted(nrm, rng);
-        float brdf = brdf_ool(c.pool.m0[slot], c.pool.m1[slot], c.pool.m2[slot], -main_d.x, -main_d.y, -main_d.z, nrm.x, nrm.y, nrm.z, nd.x, nd.y, nd.z).x;
+        float brdf = brdf_ool(q1.w, q2.w, q3.x, -main_d.x, -main_d.y, -main_d.z, nrm.x, nrm.y, nrm.z, nd.x, nd.y, nd.z).x;
         thr *= brdf * kPi;
     } else {
-        Lacc += thr * T * lr.sun_irradiance * c.pool.na[slot];
+        Lacc += thr * T * lr.sun_irradiance * q0.z;
         rng.align();
         uint4 blk = philox_block(rng.key0, rng.key1, rng.sample, rng.bounce, rng.draw >> 2);
         int used = 0;
@@ -987,7 +1065,6 @@ template <bool COUNT> DE_DEV uint32_t stage_nee_done(Ctx &c, int slot) {
         thr *= sp.w;
         rng.b0 = blk.x; rng.b1 = blk.y; rng.b2 = blk.z; rng.b3 = blk.w; rng.valid = true; rng.draw += (uint32_t)used;  // the roulette draw follows in the same block
     }
-    c.pool.L[slot] = Lacc;
     bool terminate = false;
     if (sc > 3u) {
         float p = fmaxf(0.05f, 1.0f - thr);
@@ -995,8 +1072,8 @@ template <bool COUNT> DE_DEV uint32_t stage_nee_done(Ctx &c, int slot) {
         else thr /= 1.0f - p;
     }
     ++sc;
-    if (terminate || sc >= 25u) return end_path<COUNT>(c, slot, pk, false, nd);
-    c.pool.thr[slot] = thr;
+    if (terminate || sc >= 25u) return end_path<COUNT>(c, slot, pk, false, nd, Lacc);
+    cold_st_thr_L(c, slot, thr, Lacc);
     st_d(c, slot, nd);
     pk = PK_SET_SC(pk, sc);
     DE_COUNT(c.cn, C_SEGMENTS);
@@ -1012,7 +1089,7 @@ template <bool COUNT> __global__ void __launch_bounds__(WF_WARPS * 32, 1) k_rend
     const DevDerived dv = *s.derived;
     Counters cn;
     cn.clear();
-    Ctx c{s, dv, P, pool, cn, lane};
+    Ctx c{s, dv, P, pool, cn, lane, P.cold ? P.cold + (size_t)blockIdx.x * WF_SLOTS * 4 : nullptr};
     // all slots start free (queue ST_NEW); ring entries carry lap tag 31 until first written
     for (int k = threadIdx.x; k < ST_COUNT * WF_RING; k += blockDim.x) (&pool.ring[0][0])[k] = 0xFFFFu;
     __syncthreads();
@@ -1339,6 +1416,7 @@ template <bool COUNT> __global__ void __launch_bounds__(kDeTileW * kDeTileH) k_s
 struct DeWavefrontState {
     int device = 0, sm_count = 0;
     unsigned int *d_next = nullptr;
+    float4 *d_cold = nullptr;                  // WF_COLD: shading state of the paths in flight, [sm_count][WF_SLOTS][4]
     unsigned long long *d_prof = nullptr;      // [0,32): stage profile, [32,40): launch timeline
     unsigned long long *d_cta = nullptr;       // [sm_count][24] per-CTA drain diagnostics (timeline mode)
     bool attr_set = false;
@@ -1361,6 +1439,11 @@ DeWavefrontState *de_wavefront_alloc(int device) {
     if (cudaMalloc(&st->d_prof, sizeof(unsigned long long) * 40) != cudaSuccess) { cudaFree(st->d_next); delete st; return nullptr; }
     if (cudaMalloc(&st->d_counts, sizeof(unsigned int) * 2) != cudaSuccess) { cudaFree(st->d_next); cudaFree(st->d_prof); delete st; return nullptr; }
     cudaMemset(st->d_prof, 0, sizeof(unsigned long long) * 40);
+#if WF_COLD
+    if (cudaMalloc(&st->d_cold, sizeof(float4) * 4 * (size_t)WF_SLOTS * (size_t)st->sm_count) != cudaSuccess) {
+        cudaFree(st->d_next); cudaFree(st->d_prof); cudaFree(st->d_counts); delete st; return nullptr;
+    }
+#endif
     if (cudaMalloc(&st->d_cta, sizeof(unsigned long long) * 24 * (size_t)st->sm_count) != cudaSuccess) st->d_cta = nullptr;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = numerically greatest = lowest priority
@@ -1373,6 +1456,7 @@ void de_wavefront_free(DeWavefrontState *st) {
     if (!st) return;
     cudaFree(st->d_next);
     cudaFree(st->d_prof);
+    cudaFree(st->d_cold);
     cudaFree(st->d_cls); cudaFree(st->d_wf_list); cudaFree(st->d_counts); cudaFree(st->d_cta);
     if (st->side) cudaStreamDestroy(st->side);
     if (st->ev_fork) cudaEventDestroy(st->ev_fork);
@@ -1388,7 +1472,7 @@ int de_wavefront_render(DeWavefrontState *st, const DevScene &s, const DeWavefro
         st->attr_set = true;
     }
     WfParams P;
-    P.accum = job.accum; P.accum2 = job.accum2; P.next = st->d_next;
+    P.accum = job.accum; P.accum2 = job.accum2; P.next = st->d_next; P.cold = st->d_cold;
     P.tiles_x = (job.w + kDeTileW - 1) / kDeTileW;
     const long long tiles = (long long)P.tiles_x * ((job.h + kDeTileH - 1) / kDeTileH);
     P.x0 = job.x0; P.y0 = job.y0; P.w = job.w; P.h = job.h; P.seed = job.seed;
