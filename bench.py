@@ -368,6 +368,8 @@ def main():
                          "tex_peak_source": "de_bench_tex_gather: tex2Dgather r8, L1-resident footprints, 2048 threads/SM, measured in this run",
                          "issue_active_pct": hw.get("issue_active_pct"), "lanes_per_inst": hw.get("lanes_per_inst"), "xu_pct": hw.get("xu_pct"),
                          "alu_pct": hw.get("alu_pct"), "fma_pct": hw.get("fma_pct"), "l1tex_hit_pct": hw.get("l1tex_hit_pct"), "l2_hit_pct": hw.get("l2_hit_pct"),
+                         "icache_hit_pct": hw.get("icc_hit_pct"), "gpc_icache_requests_pct_of_peak": hw.get("gcc_inst_requests_pct_of_peak"),
+                         "stall_no_instruction_per_issue": hw.get("stall_no_instruction"),
                          "hw_counter_source": hw.get("source")},
             "clocks": clocks,
         }

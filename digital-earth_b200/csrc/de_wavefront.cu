@@ -39,7 +39,7 @@ namespace de_fast {
                         // (pop, state load, one Philox block, flush, push), not the candidates.  Off; kept for the record.
 #endif
 #ifndef WF_COLD
-#define WF_COLD 0      // 1: the 13 words of a path's state that only the shading stages touch (throughput, radiance, NEE factors, main direction,
+#define WF_COLD 1      // 1: the 13 words of a path's state that only the shading stages touch (throughput, radiance, NEE factors, main direction,
                        // normal, material) live in global memory (64 B per slot, L2-resident: 148 x 2464 x 64 B = 23 MB) instead of shared
                        // memory; the pool then holds 2464 paths of 16 hot words instead of 1728 of 28.  Why: the kernel is bound by
                        // instruction fetch (profiles/r2_bench.md) and how often a stage body is re-fetched falls with the number of paths

@@ -12,6 +12,9 @@ WANT = {"issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active
         "tex_pipe_pct": "sm__inst_executed_pipe_tex.avg.pct_of_peak_sustained_active", "l1tex_hit_pct": "l1tex__t_sector_hit_rate.pct",
         "l2_hit_pct": "lts__t_sector_hit_rate.pct", "dram_read_bytes": "dram__bytes_read.sum", "dram_write_bytes": "dram__bytes_write.sum",
         "duration_ns": "gpu__time_duration.sum", "warp_inst": "smsp__inst_executed.sum", "registers": "launch__registers_per_thread",
+        "icc_hit_pct": "sm__icc_request_hit_rate.pct", "gcc_inst_requests": "gcc__cache_requests_type_instruction.sum",
+        "gcc_inst_requests_pct_of_peak": "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",
+        "stall_long_scoreboard": "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "stall_no_instruction": "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "stall_wait": "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "stall_not_selected": "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"}
