@@ -27,6 +27,21 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.de_abi_version() == 1
 
 
+def test_render_kernel_fits_the_occupancy_it_is_designed_for():
+    """The persistent kernel runs 1024 threads per SM next to a 226 KB pool: at most 64 registers per thread (65536 / 1024), a stack of a
+    few words at most (spills are shared-memory-speed traffic the design has no room for), compiled for sm_100a."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    __import__("importlib").import_module("digital_earth_b200.build").build()
+    out = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    m = re.search(r"Function \S*k_render_wavefrontILb0\S*:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert m, "k_render_wavefront<false> not found in libde.so"
+    assert int(m.group(1)) <= 64 and int(m.group(2)) <= 64, m.groups()
+
+
 def test_create_rejects_bad_resolution_without_gpu_work():
     lib = _lib.load()
     ctx = ctypes.c_void_p()

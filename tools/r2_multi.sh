@@ -1,4 +1,4 @@
-# round 2 multi-GPU evidence:  gpurun --gpus N -- 'N=<N> bash tools/r2_multi.sh'
+# round 2 multi-GPU evidence:  gpurun --gpus N -- 'N=<N> [LIGHT=1] bash tools/r2_multi.sh'   (LIGHT: spp + tile+spp lines only)
 # BASELINE configs[1] (Apollo 1080p x 1024 spp) with every partition / exchange, configs[3] (4K x 4096 spp) with spp and tile+spp,
 # and at N = 8 configs[4] (120-frame orbit, frames sharded).  Every line carries the N-GPU == 1-GPU identity check.
 cd $GRAFT_REPO_ROOT
@@ -12,10 +12,12 @@ run() {  # name, args...
 }
 run apollo_spp --steps 3 --warmup 3
 run apollo_tilespp --steps 3 --warmup 3 --partition tile+spp --tile-groups 2
-run apollo_tilespp_fused --steps 3 --warmup 3 --partition tile+spp --tile-groups 2 --exchange fused
-if [ "$N" != "2" ]; then run apollo_tile --steps 3 --warmup 3 --partition tile; fi
+if [ -z "$LIGHT" ]; then
+  run apollo_tilespp_fused --steps 3 --warmup 3 --partition tile+spp --tile-groups 2 --exchange fused
+  if [ "$N" != "2" ]; then run apollo_tile --steps 3 --warmup 3 --partition tile; fi
+fi
 run c4_tilespp --res 3840x2160 --spp 4096 --steps 2 --warmup 3 --partition tile+spp --tile-groups 2
-run c4_spp --res 3840x2160 --spp 4096 --steps 2 --warmup 3
+if [ -z "$LIGHT" ]; then run c4_spp --res 3840x2160 --spp 4096 --steps 2 --warmup 3; fi
 if [ "$N" = "8" ]; then
   P=$((P+1))
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $P -m digital_earth_b200.render \
