@@ -28,7 +28,7 @@ struct de_ctx {
     DevDerived *d_derived = nullptr;
     float *d_accum = nullptr, *d_image = nullptr;
     float *d_accum2 = nullptr;                     // optional per-pixel second moments (de_set_option "moments")
-    bool opt_space_tiles = true, opt_space_async = true, opt_timeline = false;
+    bool opt_space_tiles = true, opt_space_async = true, opt_timeline = false, opt_tile_order = true;
     unsigned long long param_version = 1;          // bumps with every de_set_params (tile classification cache key)
     uint8_t *d_cloud_max = nullptr;
     unsigned long long *d_counters = nullptr;
@@ -194,6 +194,7 @@ int de_set_option(de_ctx *ctx, const char *name, int value) {
     const std::string n(name);
     if (n == "space_tiles") ctx->opt_space_tiles = value != 0;
     else if (n == "space_async") ctx->opt_space_async = value != 0;
+    else if (n == "tile_order") ctx->opt_tile_order = value != 0;
     else if (n == "timeline") ctx->opt_timeline = value != 0;
     else if (n == "linear_textures") {
         // The row-major copies of the maps are read by the parity flavour and the test hooks only; the product integrators
@@ -339,6 +340,7 @@ int de_upload_texture(de_ctx *ctx, int slot, const uint8_t *host, int w, int h, 
         int rc_ = check_launch(ctx, "build_cloud_max");
         if (rc_) return rc_;
         ctx->scene.cloud_max = ctx->d_cloud_max; ctx->scene.cm_w = cw; ctx->scene.cm_h = ch; ctx->scene.cm_b = b;
+        ++ctx->param_version;  // the work order of the wavefront kernel looks at the cloud map (tile classification cache key)
     }
     if (slot == DE_TEX_TOPOGRAPHY) ctx->derived_dirty = true;
     CU(cudaStreamSynchronize(ctx->stream));  // host buffer may be released by the caller
@@ -397,7 +399,7 @@ static int accumulate_impl(de_ctx *ctx, int n_spp, uint32_t seed, uint32_t first
         job.accum = ctx->d_accum; job.accum2 = a2; job.n_spp = n_spp; job.seed = seed; job.first_sample = first_sample;
         job.x0 = x0; job.y0 = y0; job.w = w; job.h = h;
         job.count = ctx->counting; job.timeline = ctx->opt_timeline;
-        job.space_tiles = ctx->opt_space_tiles; job.space_async = ctx->opt_space_async;
+        job.space_tiles = ctx->opt_space_tiles; job.space_async = ctx->opt_space_async; job.tile_order = ctx->opt_tile_order;
         job.param_version = ctx->param_version;
         job.tile_stride = stride; job.tile_offset = offset;
         if (de_wavefront_render(ctx->wf, ctx->scene, job, ctx->stream) != 0) return fail(ctx, DE_ERR_NOMEM, "wavefront tile buffers: allocation failed");

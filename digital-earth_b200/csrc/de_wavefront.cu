@@ -1318,37 +1318,70 @@ DE_DEV bool tile_is_space(const DevScene &s, const DevDerived &dv, int x0, int y
     const double phi = dangle(c, axis);
     return phi > cap + alpha + 2e-5;  // NaN (degenerate camera) compares false: generic route
 }
-// one CTA; cls[t] = 1 for space tiles, 2 for tiles of another rank (tile partition: t % stride != offset), wf_list = the rest in tile
-// order, counts = {n_wf, n_space}
+// Can the paths of this tile get long?  The tail of a launch is its longest path (profiles/r2_tail.md): 15-25 segments of multiple scattering in
+// cloud, a serial chain of ~500 stage visits.  A tile all of whose corner rays meet the cloud-top sphere at more than ~20 degrees above the horizon and
+// whose lat-long footprint (padded by one cell) is empty in the dilated cloud max-map starts only clear-air / ground paths (a handful of segments).
+// f32 and approximate on purpose: this only ORDERS the work (clear tiles last), no sample depends on it.
+DE_DEV bool tile_is_clear(const DevScene &s, const DevDerived &dv, int x0, int y0, int x1, int y1) {
+    if (!s.cloud_max) return false;
+    float ulo = 2.0f, uhi = -1.0f, vlo = 2.0f, vhi = -1.0f;
+    for (int k = 0; k < 5; ++k) {
+        const float fx = k == 4 ? 0.5f * (float)(x0 + x1) : (float)((k & 1) ? x1 : x0), fy = k == 4 ? 0.5f * (float)(y0 + y1) : (float)((k & 2) ? y1 : y0);
+        const float3 d = get_cast_dir(s, dv, fx, fy, 0.0f, 0.0f);
+        const float2 hit = rsi(s.cam_pos, d, kCloudsUpper);
+        if (!(hit.x > 0.0f)) return false;                       // misses the shell, or the camera is inside it
+        const float3 p = s.cam_pos + d * hit.x;
+        if (!(-dot(p, d) > 0.35f * kCloudsUpper)) return false;  // grazing: long slant paths, the footprint test means little
+        const float2 uv = sphere_uv(p);
+        ulo = fminf(ulo, uv.x); uhi = fmaxf(uhi, uv.x); vlo = fminf(vlo, uv.y); vhi = fmaxf(vhi, uv.y);
+    }
+    if (uhi - ulo > 0.25f || vlo < 0.03f || vhi > 0.97f) return false;  // date line / polar cap
+    const float sx = (float)s.tex[3].w / (float)s.cm_b, sy = (float)s.tex[3].h / (float)s.cm_b;
+    const int cu0 = max((int)(ulo * sx) - 1, 0), cu1 = min((int)(uhi * sx) + 1, s.cm_w - 1), cv0 = max((int)(vlo * sy) - 1, 0), cv1 = min((int)(vhi * sy) + 1, s.cm_h - 1);
+    if ((cu1 - cu0 + 1) * (cv1 - cv0 + 1) > 256) return false;
+    for (int cv = cv0; cv <= cv1; ++cv)
+        for (int cu = cu0; cu <= cu1; ++cu)
+            if (__ldg(s.cloud_max + cv * s.cm_w + cu)) return false;
+    return true;
+}
+// one CTA; cls[t] = 1 for space tiles, 2 for tiles of another rank (tile partition: t % stride != offset), 0 / 3 for the persistent kernel's tiles
+// (3 = clear, see above); wf_list = the 0-tiles in tile order, then the 3-tiles in tile order; counts = {n_wf, n_space}
 __global__ void __launch_bounds__(1024) k_classify_tiles(const __grid_constant__ DevScene s, int x0, int y0, int w, int h, int tiles_x, int n_tiles, int enable,
-                                                        int stride, int offset, unsigned char *cls, unsigned int *wf_list, unsigned int *counts) {
+                                                        int order, int stride, int offset, unsigned char *cls, unsigned int *wf_list, unsigned int *counts) {
     __shared__ unsigned int warp_sum[32];
     __shared__ unsigned int base_wf, n_space;
     const DevDerived dv = *s.derived;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) { base_wf = 0u; n_space = 0u; }
     __syncthreads();
-    for (int b = 0; b < n_tiles; b += 1024) {
-        const int t = b + (int)threadIdx.x;
-        bool keep = false;
-        if (t < n_tiles) {
-            const int tx = t % tiles_x, ty = t / tiles_x;
-            const int px0 = x0 + tx * kDeTileW, py0 = y0 + ty * kDeTileH;
-            const bool mine = t % stride == offset;
-            const bool space = mine && enable && tile_is_space(s, dv, px0, py0, min(px0 + kDeTileW, x0 + w), min(py0 + kDeTileH, y0 + h));
-            cls[t] = !mine ? 2 : (space ? 1 : 0);
-            keep = mine && !space;
-            if (space) atomicAdd(&n_space, 1u);
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0 classifies and lists the tiles that may hold long paths, pass 1 appends the clear ones
+        for (int b = 0; b < n_tiles; b += 1024) {
+            const int t = b + (int)threadIdx.x;
+            bool keep = false;
+            if (t < n_tiles) {
+                unsigned char c;
+                if (pass == 0) {
+                    const int tx = t % tiles_x, ty = t / tiles_x;
+                    const int px0 = x0 + tx * kDeTileW, py0 = y0 + ty * kDeTileH, px1 = min(px0 + kDeTileW, x0 + w), py1 = min(py0 + kDeTileH, y0 + h);
+                    const bool mine = t % stride == offset;
+                    const bool space = mine && enable && tile_is_space(s, dv, px0, py0, px1, py1);
+                    const bool clear = mine && !space && order && tile_is_clear(s, dv, px0, py0, px1, py1);
+                    c = !mine ? 2 : (space ? 1 : (clear ? 3 : 0));
+                    cls[t] = c;
+                    if (space) atomicAdd(&n_space, 1u);
+                } else c = cls[t];
+                keep = c == (pass == 0 ? 0 : 3);
+            }
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+            if (lane == 0) warp_sum[wid] = __popc(bal);
+            __syncthreads();
+            unsigned int off = base_wf;
+            for (int k = 0; k < wid; ++k) off += warp_sum[k];
+            if (keep) wf_list[off + __popc(bal & ((1u << lane) - 1u))] = (unsigned)t;
+            __syncthreads();
+            if (threadIdx.x == 0) { unsigned int tot = 0u; for (int k = 0; k < 32; ++k) tot += warp_sum[k]; base_wf += tot; }
+            __syncthreads();
         }
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-        if (lane == 0) warp_sum[wid] = __popc(bal);
-        __syncthreads();
-        unsigned int off = base_wf;
-        for (int k = 0; k < wid; ++k) off += warp_sum[k];
-        if (keep) wf_list[off + __popc(bal & ((1u << lane) - 1u))] = (unsigned)t;
-        __syncthreads();
-        if (threadIdx.x == 0) { unsigned int tot = 0u; for (int k = 0; k < 32; ++k) tot += warp_sum[k]; base_wf += tot; }
-        __syncthreads();
     }
     if (threadIdx.x == 0) { counts[0] = base_wf; counts[1] = n_space; }
 }
@@ -1425,7 +1458,7 @@ struct DeWavefrontState {
     unsigned int *d_wf_list = nullptr, *d_counts = nullptr;
     int tiles_cap = 0;
     unsigned long long cls_version = ~0ull;
-    int cls_win[4] = {-1, -1, -1, -1}, cls_enable = -1, cls_part[2] = {-1, -1};
+    int cls_win[4] = {-1, -1, -1, -1}, cls_enable = -1, cls_order = -1, cls_part[2] = {-1, -1};
     // k_space_tiles runs on a side stream so its CTAs fill the SMs the persistent kernel's drain leaves idle
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1493,12 +1526,12 @@ int de_wavefront_render(DeWavefrontState *st, const DevScene &s, const DeWavefro
         st->tiles_cap = (int)tiles;
         st->cls_version = ~0ull;
     }
-    const int enable = job.space_tiles ? 1 : 0;
+    const int enable = job.space_tiles ? 1 : 0, order = job.tile_order ? 1 : 0;
     if (st->cls_version != job.param_version || st->cls_win[0] != job.x0 || st->cls_win[1] != job.y0 || st->cls_win[2] != job.w || st->cls_win[3] != job.h ||
-        st->cls_enable != enable || st->cls_part[0] != job.tile_stride || st->cls_part[1] != job.tile_offset) {
-        k_classify_tiles<<<1, 1024, 0, stream>>>(s, job.x0, job.y0, job.w, job.h, P.tiles_x, (int)tiles, enable, job.tile_stride, job.tile_offset, st->d_cls,
+        st->cls_enable != enable || st->cls_order != order || st->cls_part[0] != job.tile_stride || st->cls_part[1] != job.tile_offset) {
+        k_classify_tiles<<<1, 1024, 0, stream>>>(s, job.x0, job.y0, job.w, job.h, P.tiles_x, (int)tiles, enable, order, job.tile_stride, job.tile_offset, st->d_cls,
                                                 st->d_wf_list, st->d_counts);
-        st->cls_version = job.param_version; st->cls_enable = enable; st->cls_part[0] = job.tile_stride; st->cls_part[1] = job.tile_offset;
+        st->cls_version = job.param_version; st->cls_enable = enable; st->cls_order = order; st->cls_part[0] = job.tile_stride; st->cls_part[1] = job.tile_offset;
         st->cls_win[0] = job.x0; st->cls_win[1] = job.y0; st->cls_win[2] = job.w; st->cls_win[3] = job.h;
     }
     P.tile_list = st->d_wf_list; P.n_tiles = st->d_counts;

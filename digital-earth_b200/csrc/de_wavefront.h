@@ -12,6 +12,7 @@ struct DeWavefrontJob {
     bool timeline = false;     // with count: record the launch timeline (ramp / drain), see de_get_launch_timeline
     bool space_tiles = true;   // render tiles that cannot see the planet in k_space_tiles
     bool space_async = true;   // ... on a low-priority side stream, overlapping the persistent kernel's drain
+    bool tile_order = true;    // work order of the persistent kernel: tiles that can produce long paths (cloud in sight, limb) first, clear tiles last
     unsigned long long param_version = 0;  // bumps whenever the camera changes (tile classification cache)
     int tile_stride = 1, tile_offset = 0;  // multi-GPU tile partition: render the film tiles t of the window with t % stride == offset
 };

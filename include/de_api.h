@@ -104,6 +104,9 @@ int de_set_mode(de_ctx *ctx, int mode);
 /* integrator options (name, value); unknown names fail with DE_ERR_INVALID:
  *   "space_tiles"     1 (default) film tiles that cannot see the atmosphere shell are rendered by a dedicated converged kernel
  *   "space_async"     1 (default) ... on a side stream, overlapping the persistent kernel's drain
+ *   "tile_order"      1 (default) the persistent kernel starts with the film tiles that can produce long paths (cloud in sight, limb) and ends
+ *                     with the clear ones, so the serial tail of a launch -- its longest path -- overlaps the rest of the work.  Changes the
+ *                     order of the work only: every (pixel, sample) is the same path.
  *   "moments"         1 = keep per-pixel sums of squared sample contributions beside the accumulation buffer (image z-test,
  *                     SURVEY 8d); de_get_moment2 returns the buffer; de_reset clears it
  *   "timeline"        1 = record the wavefront kernel's launch timeline (de_get_launch_timeline); the instrumented build records
