@@ -146,7 +146,7 @@ class Renderer:
             pass
 
     def set_option(self, name, value):
-        """Integrator options of include/de_api.h (`space_tiles`, `space_async`, `moments`, `timeline`, `linear_textures`)."""
+        """Integrator options of include/de_api.h (`space_tiles`, `space_async`, `tile_order`, `moments`, `timeline`, `linear_textures`)."""
         self._bind_stream()
         self._check(self._lib.de_set_option(self._ctx, str(name).encode(), int(value)))
         if name == "moments":
