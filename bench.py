@@ -158,14 +158,41 @@ def cpu_baseline(a, steps=1, textures=None):
     return paths, times, sample, cores, tex
 
 
+def taichi_reference(a, tex):
+    """The unmodified reference on real Taichi (ti.cpu), when both are on the machine (BASELINE.md baseline B): same bounded sample as the
+    oracle port.  Returns (times, cores) or None -- neither Taichi nor the reference exist on this project's build container / GPU box."""
+    try:
+        from oracle import taichi_harness as th
+        if not th.available()[0]:
+            return None
+        cw, ch = map(int, a.cpu_res.split("x"))
+        ref = th.TaichiReference(tex, (cw, ch), archs=("cpu",))
+        try:
+            cfg = scene_cfg(a)
+            for _ in range(max(a.warmup, 0)):
+                ref.render(cfg, a.cpu_spp)
+            return [ref.render(cfg, a.cpu_spp)[1] for _ in range(a.steps)], ref.cores
+        finally:
+            ref.close()
+    except Exception as e:  # e.g. ti.Texture unsupported on the CPU backend of the installed Taichi
+        print("taichi reference unavailable (%s: %s); timing the oracle port" % (type(e).__name__, e), file=sys.stderr)
+        return None
+
+
 def run_reference(a):
-    """--impl reference: CPU implementation of the path (oracle port; Taichi is not installable here)."""
+    """--impl reference: CPU implementation of the path -- the reference itself on Taichi's CPU backend when that is installed
+    (kind "taichi"), else the oracle port (kind "port"; Taichi is not installable in this project's containers)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     paths, _, sample, cores, tex = cpu_baseline(a, steps=0)
-    _, wt, _, _, _ = cpu_baseline(a, steps=max(a.warmup, 0), textures=tex) if a.warmup else (0, [], 0, 0, 0)
-    _, times, _, _, _ = cpu_baseline(a, steps=a.steps, textures=tex)
+    kind = "port"
+    tr = taichi_reference(a, tex)
+    if tr:
+        times, cores, kind = tr[0], tr[1], "taichi"
+    else:
+        _, wt, _, _, _ = cpu_baseline(a, steps=max(a.warmup, 0), textures=tex) if a.warmup else (0, [], 0, 0, 0)
+        _, times, _, _, _ = cpu_baseline(a, steps=a.steps, textures=tex)
     total = sum(times)
     v = paths * a.steps / total
     W, H = map(int, a.res.split("x"))
@@ -175,7 +202,7 @@ def run_reference(a):
         "data": "synthetic",
         "config": {"workload": "%s (config - %s.txt), %dx%d, %d spp, synthetic %s textures" % (a.scene, SCENES[a.scene], W, H, a.spp, a.tex), "scene": a.scene,
                    "note": "CPU arm renders a bounded sample of this workload per step: " + sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
