@@ -142,6 +142,8 @@ struct WarpPool {  // CTA-wide pool, SoA: lane l touching slot s hits bank s%32
     unsigned long long t_exhaust, t_few;  // ... when it did, and when fewer than 64 of its paths were still alive
 };
 
+static_assert(sizeof(WarpPool) <= 227 * 1024, "the pool must fit the 227 KB of shared memory a CTA can opt into on sm_100");
+
 struct WfParams {
     float *accum;
     float4 *cold;        // WF_COLD: [gridDim.x][WF_SLOTS][4] shading state of the paths in flight
