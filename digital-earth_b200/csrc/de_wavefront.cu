@@ -4,8 +4,11 @@
 // active per issued instruction -- path length and stage mix diverge, memory does not matter
 // (L1 97 %, L2 98 % hits, DRAM idle).  This kernel keeps every lane of a warp inside the SAME
 // inner loop:
-//   * one persistent CTA per SM owns a pool of WF_SLOTS path states in shared memory (SoA,
-//     112 B per path), so path state never touches HBM;
+//   * one persistent CTA per SM owns a pool of WF_SLOTS (2464) path states: the 16 words every stage needs in shared
+//     memory (SoA, 64 B per path), the 13 words only the shading stages touch as one 64-B record per path in global
+//     memory that stays in L2 (WF_COLD) -- path state never touches HBM, and the pool is large enough for the stage
+//     queues to hold several groups, which is what keeps a stage body in the 32 KB instruction cache between visits
+//     (the kernel is bound by instruction fetch: profiles/r2_bench.md);
 //   * a path is a small state machine  SDF -> SDF_DONE -> RMO -> RMO_DONE -> CLOUD -> EVENT ->
 //     (SURFACE -> SDF ->) RMO -> RMO_DONE -> CLOUD -> NEE_DONE -> SDF ...  (pathtracer.py:349-453 cut
 //     at its loop boundaries); every stage has a ring queue of ready slots in shared memory;
